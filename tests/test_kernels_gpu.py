@@ -1,0 +1,273 @@
+"""Per-kernel parity on the GPU: each hand-written sm_100a kernel against the matching torch fp32 op on
+fp16-rounded inputs.  Shapes follow SURVEY.md Appendix A plus ragged tails."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _rel(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _randn(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale)
+
+
+# ------------------------------------------------------------------------------------------- igemm: linear
+@pytest.mark.parametrize("m,k,n", [(128, 64, 128), (256, 320, 320), (1000, 1280, 1280), (24, 2048, 640),
+                                   (8, 320, 1280), (4096, 640, 960), (300, 128, 16), (512, 1280, 5120)])
+def test_linear_matches_torch(udt_lib, m, k, n):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(m * 7 + k + n)
+    x = _randn((m, k), g).half()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).half()
+    b = _randn((n,), g)
+    ref = x.float() @ w.float().t() + b
+    y = ops.linear(x.to(dev), w.to(dev), b.to(dev))
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 2e-3
+    # fp32 output + residual + silu variants
+    r = _randn((m, n), g).half()
+    y2 = ops.linear(x.to(dev), w.to(dev), b.to(dev), residual=r.to(dev), act=ops.UDT_ACT_SILU, out_fp32=True)
+    ref2 = F.silu(ref) + r.float()
+    torch.cuda.synchronize()
+    assert _rel(y2.cpu(), ref2) < 2e-3
+
+
+@pytest.mark.parametrize("bn", [16, 32, 64, 96, 128, 160, 192, 224, 256])
+def test_linear_all_column_tiles(udt_lib, bn):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(bn)
+    m, k, n = 384, 192, 3 * bn - 8
+    x = _randn((m, k), g).half()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).half()
+    ref = x.float() @ w.float().t()
+    y = ops.linear(x.to(dev), w.to(dev), bn_hint=bn)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 2e-3
+
+
+def test_geglu_epilogue(udt_lib):
+    from udifftext_b200 import ops, pack
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    m, c = 512, 320
+    x = _randn((m, c), g).half()
+    w = _randn((8 * c, c), g, 1 / math.sqrt(c))
+    b = _randn((8 * c,), g, 0.1)
+    wp, bp = pack.pack_geglu(w, b)
+    h = x.float() @ w.half().float().t() + b
+    a, gate = h.chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    y = ops.linear(x.to(dev), wp.to(dev), bp.to(dev), act=ops.UDT_ACT_GEGLU)
+    torch.cuda.synchronize()
+    assert y.shape == (m, 4 * c)
+    assert _rel(y.cpu(), ref) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------- igemm: conv3x3
+@pytest.mark.parametrize("nb,h,w,cin,cout", [(2, 64, 64, 64, 64), (2, 32, 32, 320, 640), (3, 16, 16, 640, 320),
+                                             (3, 8, 8, 1280, 1280), (1, 24, 24, 128, 192), (2, 12, 20, 64, 4),
+                                             (1, 128, 256, 64, 128)])
+def test_conv3x3_matches_torch(udt_lib, nb, h, w, cin, cout):
+    from udifftext_b200 import ops, pack
+    dev = _dev()
+    g = torch.Generator().manual_seed(nb + h + cin + cout)
+    x = _randn((nb, cin, h, w), g).half()
+    wt = _randn((cout, cin, 3, 3), g, 1 / math.sqrt(9 * cin)).half()
+    b = _randn((cout,), g)
+    rb = _randn((nb, cout), g)
+    ref = F.conv2d(x.float(), wt.float(), b, padding=1) + rb[:, :, None, None]
+    xh = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    y = ops.conv3x3(xh, pack.pack_conv3x3(wt.float()).to(dev), b.to(dev), rowbias=rb.to(dev), out_fp32=(cout < 8))
+    torch.cuda.synchronize()
+    assert _rel(y.float().cpu().permute(0, 3, 1, 2), ref) < 2e-3
+
+
+def test_conv3x3_fused_skip_and_residual(udt_lib):
+    """ResBlock tail: conv2(h) + skip_1x1(cat(a, b)) as extra K segments; and identity residual."""
+    from udifftext_b200 import ops, pack
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    nb, hh, ww, c, ca, cb = 2, 16, 16, 320, 640, 320
+    h = _randn((nb, c, hh, ww), g).half()
+    a = _randn((nb, ca, hh, ww), g).half()
+    b_ = _randn((nb, cb, hh, ww), g).half()
+    w2 = _randn((c, c, 3, 3), g, 1 / math.sqrt(9 * c)).half()
+    ws = _randn((c, ca + cb, 1, 1), g, 1 / math.sqrt(ca + cb)).half()
+    bias = _randn((c,), g)
+    ref = F.conv2d(h.float(), w2.float(), None, padding=1) + F.conv2d(torch.cat([a, b_], 1).float(), ws.float()) + bias[None, :, None, None]
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(dev)
+    wp = pack.pack_conv3x3(w2.float(), [ws.float()]).to(dev)
+    y = ops.conv3x3(nhwc(h), wp, bias.to(dev), skip_srcs=[nhwc(a), nhwc(b_)])
+    torch.cuda.synchronize()
+    assert _rel(y.float().cpu().permute(0, 3, 1, 2), ref) < 2e-3
+    res = _randn((nb, c, hh, ww), g).half()
+    y2 = ops.conv3x3(nhwc(h), pack.pack_conv3x3(w2.float()).to(dev), bias.to(dev), residual=nhwc(res))
+    ref2 = F.conv2d(h.float(), w2.float(), bias, padding=1) + res.float()
+    torch.cuda.synchronize()
+    assert _rel(y2.float().cpu().permute(0, 3, 1, 2), ref2) < 2e-3
+
+
+@pytest.mark.parametrize("stride,pad_lo,cin", [(1, 1, 9), (2, 1, 64), (2, 0, 32)])
+def test_im2col_conv_paths(udt_lib, stride, pad_lo, cin):
+    """first conv (Cin=9), UNet stride-2 (pad 1) and VAE stride-2 (pad (0,1,0,1)) through im2col + GEMM."""
+    from udifftext_b200 import ops, pack
+    dev = _dev()
+    g = torch.Generator().manual_seed(stride * 10 + cin)
+    nb, h, w, cout = 2, 32, 32, 128
+    x = _randn((nb, cin, h, w), g).half()
+    wt = _randn((cout, cin, 3, 3), g, 1 / math.sqrt(9 * cin)).half()
+    if pad_lo == 0:
+        ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wt.float(), None, stride=2)
+    else:
+        ref = F.conv2d(x.float(), wt.float(), None, stride=stride, padding=1)
+    ho, wo = ref.shape[2], ref.shape[3]
+    cpad = (cin + 7) // 8 * 8
+    xh = torch.zeros((nb, h, w, cpad), dtype=torch.float16)
+    xh[..., :cin] = x.permute(0, 2, 3, 1)
+    kpad = (9 * cpad + 63) // 64 * 64
+    wpad = torch.zeros((cout, cpad, 3, 3))
+    wpad[:, :cin] = wt.float()
+    cols = ops.im2col3x3(xh.to(dev), stride, pad_lo, ho, wo, kpad)
+    y = ops.linear(cols, pack.pack_conv3x3_padded(wpad, kpad).to(dev))
+    torch.cuda.synchronize()
+    assert _rel(y.float().cpu().reshape(nb, ho, wo, cout).permute(0, 3, 1, 2), ref) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("nb,hw,c0,c1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (3, 1024, 640, 320, True, 1e-5),
+                                                  (2, 64, 1280, 1280, True, 1e-5), (2, 256, 1280, 0, False, 1e-6),
+                                                  (1, 4096, 128, 0, True, 1e-6), (2, 100, 64, 0, False, 1e-6)])
+def test_groupnorm_matches_torch(udt_lib, nb, hw, c0, c1, silu, eps):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(hw + c0 + c1)
+    c = c0 + c1
+    x = (_randn((nb, hw, c), g) * 2 + 0.5).half()
+    gamma = _randn((c,), g) * 0.5 + 1
+    beta = _randn((c,), g) * 0.5
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    x0 = x[..., :c0].contiguous().to(dev)
+    x1 = x[..., c0:].contiguous().to(dev) if c1 else None
+    y = ops.groupnorm(x0, gamma.to(dev), beta.to(dev), eps, silu, x1=x1)
+    torch.cuda.synchronize()
+    assert (y.float().cpu() - ref).abs().max().item() < 2e-2
+    assert _rel(y.cpu(), ref) < 1.5e-3
+
+
+@pytest.mark.parametrize("rows,c", [(4096, 320), (1000, 640), (77, 1280), (24, 2048)])
+def test_layernorm_matches_torch(udt_lib, rows, c):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(rows + c)
+    x = (_randn((rows, c), g) * 3 + 1).half()
+    gamma = _randn((c,), g) * 0.5 + 1
+    beta = _randn((c,), g) * 0.5
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    y = ops.layernorm(x.to(dev), gamma.to(dev), beta.to(dev), 1e-5)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 1.5e-3
+
+
+# ------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("b,n,heads", [(2, 4096, 5), (3, 1024, 10), (2, 256, 20), (2, 64, 20), (1, 576, 3), (1, 144, 2)])
+def test_fmha_matches_torch(udt_lib, b, n, heads):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(n + heads)
+    c = heads * 64
+    qkv = _randn((b * n, 3 * c), g).half()
+    q, k, v = (qkv[:, i * c:(i + 1) * c].float().reshape(b, n, heads, 64).permute(0, 2, 1, 3) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(b * n, c)
+    d = qkv.to(dev)
+    y = ops.fmha(d[:, :c], d[:, c:2 * c], d[:, 2 * c:], b, n, n, heads, 64 ** -0.5)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("b,n,heads,l", [(2, 4096, 5, 12), (2, 300, 10, 12), (1, 64, 20, 1), (2, 256, 20, 7)])
+def test_xattn_small_l_matches_torch(udt_lib, b, n, heads, l):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(n + heads + l)
+    c = heads * 64
+    q = _randn((b * n, c), g).half()
+    k = _randn((b * l, c), g).half()
+    v = _randn((b * l, c), g).half()
+    split = lambda t, s: t.float().reshape(b, s, heads, 64).permute(0, 2, 1, 3).reshape(b * heads, s, 64)
+    sim = torch.einsum("bid,bjd->bij", split(q, n), split(k, l)) * 0.125
+    pr = sim.softmax(-1) if l > 1 else sim.sigmoid()
+    ref = torch.einsum("bij,bjd->bid", pr, split(v, l)).reshape(b, heads, n, 64).permute(0, 2, 1, 3).reshape(b * n, c)
+    probs = torch.empty((b * heads, n, l), device=dev, dtype=torch.float32)
+    y = ops.xattn_small_l(q.to(dev), k.to(dev), v.to(dev), b, n, l, heads, 0.125, probs=probs)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 2e-3
+    assert (probs.cpu() - pr).abs().max().item() < 1e-4
+
+
+def test_softmax_rows(udt_lib):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    x = (_randn((300, 4096), g) * 20).half()
+    ref = (x.float() * 0.0442).softmax(-1)
+    y = ops.softmax_rows_(x.to(dev), 0.0442)
+    torch.cuda.synchronize()
+    assert (y.float().cpu() - ref).abs().max().item() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------- glue
+def test_sampler_glue_and_layout(udt_lib):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    b, hw = 3, 4096
+    x = _randn((b, hw, 4), g)
+    cu = _randn((b, hw, 5), g)
+    cc = _randn((b, hw, 5), g)
+    out = torch.empty((2 * b, hw, 16), device=dev, dtype=torch.float16)
+    ops.cfg_pack(x.to(dev), cu.to(dev), cc.to(dev), 0.37, out)
+    ref = torch.zeros((2 * b, hw, 16))
+    ref[:b, :, :4] = x * 0.37
+    ref[b:, :, :4] = x * 0.37
+    ref[:b, :, 4:9] = cu
+    ref[b:, :, 4:9] = cc
+    torch.cuda.synchronize()
+    assert (out.float().cpu() - ref.half().float()).abs().max().item() == 0.0
+    eps = _randn((2 * b, hw, 4), g)
+    xd = x.to(dev).clone()
+    ops.cfg_euler_step_(xd, eps.to(dev), 5.0, -0.3)
+    ref2 = x + (-0.3) * (eps[:b] + 5.0 * (eps[b:] - eps[:b]))
+    torch.cuda.synchronize()
+    assert (xd.cpu() - ref2).abs().max().item() < 1e-5
+    # layout conversions + upsample
+    a = _randn((2, 9, 8, 12), g)
+    nh = ops.nchw_to_nhwc_f16(a.to(dev), cpad=16)
+    torch.cuda.synchronize()
+    assert (nh[..., :9].float().cpu() - a.permute(0, 2, 3, 1).half().float()).abs().max().item() == 0.0
+    assert nh[..., 9:].abs().max().item() == 0.0
+    back = ops.nhwc_to_nchw_f32(nh, 9, scale=0.5, shift=0.5, clamp01=True)
+    torch.cuda.synchronize()
+    assert (back.cpu() - (a.half().float() * 0.5 + 0.5).clamp(0, 1)).abs().max().item() < 1e-6
+    t = _randn((2, 5, 7, 64), g).half()
+    up = ops.upsample2x(t.to(dev))
+    refu = F.interpolate(t.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert (up.float().cpu() - refu).abs().max().item() == 0.0

@@ -1,0 +1,382 @@
+// udt_elem.cu — HBM-bound glue kernels of the hot path: K5 short-context cross-attention, row softmax,
+// K7 CFG pack / Euler step, nearest 2x upsample, im2col for the rare convs outside the TMA path, and the
+// NCHW fp32 <-> NHWC fp16 conversions at the API boundary.  All 16-byte vectorised where the layout allows.
+#include "udt_common.cuh"
+#include "udt_host.h"
+
+namespace {
+
+using namespace udt;
+
+// ---------------------------------------------------------------------------------------------- K5
+// One thread per (query pixel, head): q row (64 fp16 = 128 B) against L <= 16 context tokens whose K/V
+// (L x 64 each) are staged in shared memory as fp32.  Replaces attention.py:147-174.
+constexpr int kXaMaxL = 16;
+constexpr int kXaThreads = 128;
+
+__global__ void __launch_bounds__(kXaThreads) xattn_small_l_kernel(const __half* __restrict__ q,
+                                                                   const __half* __restrict__ kc,
+                                                                   const __half* __restrict__ vc,
+                                                                   __half* __restrict__ o, float* __restrict__ probs,
+                                                                   int N, int L, int heads, int ldq, int ldkv, int ldo,
+                                                                   float scale) {
+  __shared__ float sk[kXaMaxL * 64];
+  __shared__ float sv[kXaMaxL * 64];
+  const int b = blockIdx.z;
+  const int h = blockIdx.y;
+  for (int i = threadIdx.x; i < L * 64; i += blockDim.x) {
+    const int l = i / 64, d = i % 64;
+    const size_t off = (static_cast<size_t>(b) * L + l) * ldkv + h * 64 + d;
+    sk[i] = __half2float(kc[off]);
+    sv[i] = __half2float(vc[off]);
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t row = static_cast<size_t>(b) * N + n;
+  float qf[64];
+  const uint4* q4 = reinterpret_cast<const uint4*>(q + row * ldq + h * 64);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const uint4 t = __ldg(q4 + v);
+    const __half2* hh = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(hh[j]);
+      qf[v * 8 + 2 * j] = f.x;
+      qf[v * 8 + 2 * j + 1] = f.y;
+    }
+  }
+  float s[kXaMaxL];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int l = 0; l < kXaMaxL; ++l) {
+    if (l < L) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) acc += qf[d] * sk[l * 64 + d];
+      s[l] = acc * scale;
+      mx = fmaxf(mx, s[l]);
+    }
+  }
+  if (L > 1) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int l = 0; l < kXaMaxL; ++l)
+      if (l < L) {
+        s[l] = __expf(s[l] - mx);
+        sum += s[l];
+      }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int l = 0; l < kXaMaxL; ++l)
+      if (l < L) s[l] *= inv;
+  } else {
+    s[0] = 1.0f / (1.0f + __expf(-s[0]));  // sigmoid on a single token (attention.py:159-162)
+  }
+  if (probs != nullptr) {
+    float* pr = probs + ((static_cast<size_t>(b) * heads + h) * N + n) * L;
+    for (int l = 0; l < L; ++l) pr[l] = s[l];
+  }
+  float of[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) of[d] = 0.0f;
+#pragma unroll
+  for (int l = 0; l < kXaMaxL; ++l) {
+    if (l < L) {
+#pragma unroll
+      for (int d = 0; d < 64; ++d) of[d] += s[l] * sv[l * 64 + d];
+    }
+  }
+  uint4* o4 = reinterpret_cast<uint4*>(o + row * ldo + h * 64);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    uint4 ov;
+    ov.x = pack_half2(of[v * 8 + 0], of[v * 8 + 1]);
+    ov.y = pack_half2(of[v * 8 + 2], of[v * 8 + 3]);
+    ov.z = pack_half2(of[v * 8 + 4], of[v * 8 + 5]);
+    ov.w = pack_half2(of[v * 8 + 6], of[v * 8 + 7]);
+    o4[v] = ov;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- row softmax
+// One CTA per row; cols up to 16384 (VAE attention N = 4096 / 9216), values cached in registers.
+constexpr int kSmThreads = 256;
+constexpr int kSmMaxVec = 8;  // 256 threads * 8 vec * 8 halves = 16384 columns
+
+__global__ void __launch_bounds__(kSmThreads) softmax_rows_kernel(__half* __restrict__ x, int cols, int ld, float scale) {
+  __shared__ float red[kSmThreads / 32];
+  __half* xr = x + static_cast<size_t>(blockIdx.x) * ld;
+  const int VC = cols / 8;
+  uint4 v[kSmMaxVec];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSmMaxVec; ++i) {
+    const int vc = threadIdx.x + i * kSmThreads;
+    if (vc < VC) {
+      v[i] = *reinterpret_cast<const uint4*>(xr + vc * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        mx = fmaxf(mx, fmaxf(f.x, f.y));
+      }
+    }
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < kSmThreads / 32; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float e[kSmMaxVec][8];
+  float sum = 0.0f;
+  const float sl2 = scale * 1.4426950408889634f;
+#pragma unroll
+  for (int i = 0; i < kSmMaxVec; ++i) {
+    const int vc = threadIdx.x + i * kSmThreads;
+    if (vc < VC) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        e[i][2 * j] = exp2f((f.x - mx) * sl2);
+        e[i][2 * j + 1] = exp2f((f.y - mx) * sl2);
+        sum += e[i][2 * j] + e[i][2 * j + 1];
+      }
+    }
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kSmThreads / 32; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < kSmMaxVec; ++i) {
+    const int vc = threadIdx.x + i * kSmThreads;
+    if (vc < VC) {
+      uint4 ov;
+      ov.x = pack_half2(e[i][0] * inv, e[i][1] * inv);
+      ov.y = pack_half2(e[i][2] * inv, e[i][3] * inv);
+      ov.z = pack_half2(e[i][4] * inv, e[i][5] * inv);
+      ov.w = pack_half2(e[i][6] * inv, e[i][7] * inv);
+      *reinterpret_cast<uint4*>(xr + vc * 8) = ov;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K7
+// unet_in[2B, HW, 16] fp16: rows [0,B) = uc half, [B,2B) = cond half (guiders.py:36: uc first).
+__global__ void cfg_pack_kernel(const float* __restrict__ x, const float* __restrict__ cat_uc,
+                                const float* __restrict__ cat_c, __half* __restrict__ out, int B, int HW, float c_in) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 2B*HW pixels
+  const int total = 2 * B * HW;
+  if (idx >= total) return;
+  const int half_sel = idx / (B * HW);
+  const int pix = idx % (B * HW);
+  const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(pix) * 4);
+  const float* cc = (half_sel == 0 ? cat_uc : cat_c) + static_cast<size_t>(pix) * 5;
+  float f[16];
+  f[0] = xv.x * c_in;
+  f[1] = xv.y * c_in;
+  f[2] = xv.z * c_in;
+  f[3] = xv.w * c_in;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) f[4 + j] = cc[j];
+#pragma unroll
+  for (int j = 9; j < 16; ++j) f[j] = 0.0f;
+  uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * 16);
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    uint4 ov;
+    ov.x = pack_half2(f[v * 8 + 0], f[v * 8 + 1]);
+    ov.y = pack_half2(f[v * 8 + 2], f[v * 8 + 3]);
+    ov.z = pack_half2(f[v * 8 + 4], f[v * 8 + 5]);
+    ov.w = pack_half2(f[v * 8 + 6], f[v * 8 + 7]);
+    o4[v] = ov;
+  }
+}
+
+// x[B,HW,4] += dsigma * (eps_u + s*(eps_c - eps_u)); eps2b fp32 [2B,HW,4]
+__global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps, int B, int HW, float s,
+                                 float dsigma) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = B * HW;
+  if (idx >= total) return;
+  float4 xv = *reinterpret_cast<float4*>(x + static_cast<size_t>(idx) * 4);
+  const float4 eu = *reinterpret_cast<const float4*>(eps + static_cast<size_t>(idx) * 4);
+  const float4 ec = *reinterpret_cast<const float4*>(eps + (static_cast<size_t>(total) + idx) * 4);
+  xv.x += dsigma * (eu.x + s * (ec.x - eu.x));
+  xv.y += dsigma * (eu.y + s * (ec.y - eu.y));
+  xv.z += dsigma * (eu.z + s * (ec.z - eu.z));
+  xv.w += dsigma * (eu.w + s * (ec.w - eu.w));
+  *reinterpret_cast<float4*>(x + static_cast<size_t>(idx) * 4) = xv;
+}
+
+// ---------------------------------------------------------------------------------------------- movement
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int NB, int H, int W, int VC) {
+  const size_t total = static_cast<size_t>(NB) * (2 * H) * (2 * W) * VC;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int vc = static_cast<int>(i % VC);
+    size_t r = i / VC;
+    const int ox = static_cast<int>(r % (2 * W));
+    r /= (2 * W);
+    const int oy = static_cast<int>(r % (2 * H));
+    const int n = static_cast<int>(r / (2 * H));
+    y[i] = __ldg(x + ((static_cast<size_t>(n) * H + (oy >> 1)) * W + (ox >> 1)) * VC + vc);
+  }
+}
+
+// out[(n,oy,ox), tap*C + c] = x[n, oy*stride - pad_lo + ky, ox*stride - pad_lo + kx, c]; columns >= 9*C zero.
+__global__ void im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ out, int NB, int H, int W, int C,
+                                 int ld, int stride, int pad_lo, int Ho, int Wo, int Kpad) {
+  const size_t total = static_cast<size_t>(NB) * Ho * Wo * Kpad;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kpad);
+    size_t r = i / Kpad;
+    const int ox = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oy = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    __half v = __float2half(0.0f);
+    if (k < 9 * C) {
+      const int tap = k / C, c = k % C;
+      const int iy = oy * stride - pad_lo + tap / 3;
+      const int ix = ox * stride - pad_lo + tap % 3;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<size_t>(n) * H + iy) * W + ix) * ld + c];
+    }
+    out[i] = v;
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restrict__ y, int NB, int C, int HW, int Cpad) {
+  const size_t total = static_cast<size_t>(NB) * HW * Cpad;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cpad);
+    const size_t r = i / Cpad;
+    const int p = static_cast<int>(r % HW);
+    const int n = static_cast<int>(r / HW);
+    y[i] = (c < C) ? __float2half_rn(x[(static_cast<size_t>(n) * C + c) * HW + p]) : __float2half(0.0f);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int is_f32, float* __restrict__ y, int NB, int C, int HW,
+                                    int ld, float scale, float shift, int clamp01) {
+  const size_t total = static_cast<size_t>(NB) * C * HW;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i % HW);
+    const size_t r = i / HW;
+    const int c = static_cast<int>(r % C);
+    const int n = static_cast<int>(r / C);
+    const size_t src = (static_cast<size_t>(n) * HW + p) * ld + c;
+    float v = is_f32 ? reinterpret_cast<const float*>(x)[src] : __half2float(reinterpret_cast<const __half*>(x)[src]);
+    v = v * scale + shift;
+    if (clamp01) v = fminf(fmaxf(v, 0.0f), 1.0f);
+    y[i] = v;
+  }
+}
+
+inline int grid_for(size_t total, int threads) {
+  size_t g = (total + threads - 1) / threads;
+  const size_t cap = 148 * 32;
+  return static_cast<int>(g < cap ? (g == 0 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+using udt_host::check_launch;
+using udt_host::fail;
+using udt_host::require_sm100;
+
+extern "C" int udt_xattn_small_l(const void* q, const void* kc, const void* vc, void* o, float* probs, int32_t B,
+                                 int32_t N, int32_t L, int32_t heads, int32_t ldq, int32_t ldkv, int32_t ldo,
+                                 float scale, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (L < 1 || L > kXaMaxL) return fail(UDT_ERR_SHAPE, "udt_xattn_small_l: L=%d (1..%d)", L, kXaMaxL);
+  if (ldq % 8 || ldo % 8) return fail(UDT_ERR_ALIGN, "udt_xattn_small_l: ldq/ldo must be multiples of 8");
+  dim3 grid((N + kXaThreads - 1) / kXaThreads, heads, B);
+  xattn_small_l_kernel<<<grid, kXaThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(kc), reinterpret_cast<const __half*>(vc),
+      reinterpret_cast<__half*>(o), probs, N, L, heads, ldq, ldkv, ldo, scale);
+  return check_launch("udt_xattn_small_l");
+}
+
+extern "C" int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (cols % 8 || ld % 8 || cols > kSmThreads * kSmMaxVec * 8 || cols < 8)
+    return fail(UDT_ERR_SHAPE, "udt_softmax_rows: cols=%d ld=%d unsupported", cols, ld);
+  softmax_rows_kernel<<<rows, kSmThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<__half*>(x), cols,
+                                                                                       ld, scale);
+  return check_launch("udt_softmax_rows");
+}
+
+extern "C" int udt_cfg_pack(const float* x, const float* concat_uc, const float* concat_c, void* unet_in, int32_t B,
+                            int32_t HW, float c_in, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  const int total = 2 * B * HW;
+  cfg_pack_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, concat_uc, concat_c, reinterpret_cast<__half*>(unet_in), B, HW, c_in);
+  return check_launch("udt_cfg_pack");
+}
+
+extern "C" int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32_t HW, float cfg_scale, float dsigma,
+                                  void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  const int total = B * HW;
+  cfg_euler_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, eps2b, B, HW, cfg_scale,
+                                                                                          dsigma);
+  return check_launch("udt_cfg_euler_step");
+}
+
+extern "C" int udt_upsample2x_nhwc(const void* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (C % 8) return fail(UDT_ERR_SHAPE, "udt_upsample2x_nhwc: C=%d not a multiple of 8", C);
+  const size_t total = static_cast<size_t>(NB) * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), NB, H, W, C / 8);
+  return check_launch("udt_upsample2x_nhwc");
+}
+
+extern "C" int udt_im2col3x3_nhwc(const void* x, void* out, int32_t NB, int32_t H, int32_t W, int32_t C, int32_t ld,
+                                  int32_t stride, int32_t pad_lo, int32_t Ho, int32_t Wo, int32_t Kpad, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (Kpad < 9 * C || Kpad % 8) return fail(UDT_ERR_SHAPE, "udt_im2col3x3_nhwc: Kpad=%d < 9*C=%d", Kpad, 9 * C);
+  const size_t total = static_cast<size_t>(NB) * Ho * Wo * Kpad;
+  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), NB, H, W, C, ld, stride, pad_lo, Ho, Wo, Kpad);
+  return check_launch("udt_im2col3x3_nhwc");
+}
+
+extern "C" int udt_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t NB, int32_t C, int32_t HW, int32_t Cpad,
+                                        void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  const size_t total = static_cast<size_t>(NB) * HW * Cpad;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__half*>(y), NB, C, HW, Cpad);
+  return check_launch("udt_nchw_f32_to_nhwc_f16");
+}
+
+extern "C" int udt_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* y, int32_t NB, int32_t C, int32_t HW,
+                                    int32_t ld, float scale, float shift, int32_t clamp01, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  const size_t total = static_cast<size_t>(NB) * C * HW;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, x_is_fp32, y, NB, C, HW, ld, scale, shift, clamp01);
+  return check_launch("udt_nhwc_to_nchw_f32");
+}

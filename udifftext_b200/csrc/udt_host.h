@@ -1,0 +1,28 @@
+// udt_host.h — host-side helpers shared by the C-ABI translation units (error reporting, device query,
+// TMA tensor-map encoding through the driver entry point so the library does not link libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/udt_api.h"
+
+namespace udt_host {
+
+char* error_buffer();  // thread-local, 512 bytes
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);   // cudaGetLastError -> UDT_ERR_LAUNCH
+int require_sm100();                  // UDT_OK or UDT_ERR_ARCH (cached per device)
+int num_sms();
+int arch();                           // compute capability * 10 of the current device, or <0
+
+// 2-D fp16 tensor map, dim0 = contiguous (cols), box = {box0, box1}, 128B swizzle.
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box0,
+                 uint32_t box1);
+// 4-D fp16 NHWC tensor map: dims (C, W, H, N), channel pitch `ld` elements, box = {64, bw, bh, bn}, 128B swizzle.
+int make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld,
+                   uint32_t bw, uint32_t bh, uint32_t bn);
+
+}  // namespace udt_host

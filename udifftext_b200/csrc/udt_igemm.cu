@@ -1,0 +1,453 @@
+// udt_igemm.cu — K2/K3: segmented implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   out[m, n] = act( sum_{seg,tap,c} A_seg[pixel(m) + tap, c] * Wt[n, k] + bias[n] + rowbias[img(m), n] ) + res[m, n]
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   : per K step one 4-D box load {64 ch, bw, bh, bn} of the NHWC activation
+//                                (shifted by the 3x3 tap, out-of-bounds zero filled = conv padding) and one
+//                                2-D box load {64, BN} of the K-major fp16 weights, both 128B-swizzled.
+//   warp 1      MMA issuer     : tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16, fp32 accumulators
+//                                in TMEM, two accumulator buffers so the epilogue of tile i overlaps tile i+1.
+//   warps 2..5  epilogue       : tcgen05.ld (thread = output row), bias / per-image bias / SiLU / GEGLU /
+//                                residual, fp16 (or fp32) stores straight to global memory.
+// Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+//
+// Replaces the cuDNN / cuBLAS call sites listed in include/udt_api.h (udt_igemm).
+#include "udt_common.cuh"
+#include "udt_host.h"
+
+namespace {
+
+using namespace udt;
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                         // fp16 elements per K step = one 128B swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;                     // TMEM column offset of the second accumulator
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kCtrlBytes = 1024;
+constexpr int kGegluTile = 128;
+
+struct IGemmParams {
+  CUtensorMap mapA[3];
+  CUtensorMap mapB;
+  int32_t seg_kc[3];
+  int32_t seg_taps[3];
+  int32_t nseg, ksteps;
+  int32_t W, H, NB;
+  int32_t bw, bh, bn;
+  int32_t tiles_w, tiles_h, tiles_nb, tiles_n, num_tiles;
+  int32_t N_out, BN, stages;
+  const float* bias;
+  const float* rowbias;
+  const __half* residual;
+  int32_t ldr;
+  void* out;
+  int32_t ldo, out_fp32, act;
+};
+
+struct TileCoord {
+  int w0, h0, n0, n_blk;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int tile) {
+  TileCoord t;
+  t.n_blk = tile % p.tiles_n;
+  int m_blk = tile / p.tiles_n;
+  int tw = m_blk % p.tiles_w;
+  int r = m_blk / p.tiles_w;
+  int th = r % p.tiles_h;
+  int tn = r / p.tiles_h;
+  t.w0 = tw * p.bw;
+  t.h0 = th * p.bh;
+  t.n0 = tn * p.bn;
+  return t;
+}
+
+// Finish `cnt` (<= 32) consecutive output columns of one row: f[] holds the fp32 accumulators.
+__device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[32], int cnt, size_t m, int img,
+                                               int col, bool fast) {
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cnt) f[j] += __ldg(p.bias + col + j);
+  }
+  if (p.rowbias != nullptr) {
+    const float* rb = p.rowbias + static_cast<size_t>(img) * p.N_out + col;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cnt) f[j] += __ldg(rb + j);
+  }
+  if (p.act == UDT_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+  }
+  if (p.out_fp32) {
+    float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col;
+    if (p.residual != nullptr) {
+      const __half* r = p.residual + m * p.ldr + col;
+      for (int j = 0; j < cnt; ++j) f[j] += __half2float(r[j]);
+    }
+    for (int j = 0; j < cnt; ++j) o[j] = f[j];
+    return;
+  }
+  __half* o = reinterpret_cast<__half*>(p.out) + m * p.ldo + col;
+  if (fast && cnt == 32) {
+    if (p.residual != nullptr) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint4 rv = r4[v];
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 rf = __half22float2(rh[j]);
+          f[v * 8 + 2 * j] += rf.x;
+          f[v * 8 + 2 * j + 1] += rf.y;
+        }
+      }
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      uint4 ov;
+      ov.x = pack_half2(f[v * 8 + 0], f[v * 8 + 1]);
+      ov.y = pack_half2(f[v * 8 + 2], f[v * 8 + 3]);
+      ov.z = pack_half2(f[v * 8 + 4], f[v * 8 + 5]);
+      ov.w = pack_half2(f[v * 8 + 6], f[v * 8 + 7]);
+      o4[v] = ov;
+    }
+    return;
+  }
+  if (p.residual != nullptr) {
+    const __half* r = p.residual + m * p.ldr + col;
+    for (int j = 0; j < cnt; ++j) f[j] += __half2float(r[j]);
+  }
+  for (int j = 0; j < cnt; ++j) o[j] = __float2half_rn(f[j]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_constant__ IGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base = smem_raw + (base_addr - raw_addr);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int b_bytes = p.BN * kBlockK * 2;
+  uint8_t* sA = base + kCtrlBytes;
+  uint8_t* sB = sA + p.stages * kABytes;
+  const uint32_t sA_addr = base_addr + kCtrlBytes;
+  const uint32_t sB_addr = sA_addr + p.stages * kABytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.mapA[s]);
+    tma_prefetch_desc(&p.mapB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        int kstep = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const CUtensorMap* ma = &p.mapA[s];
+          const int taps = p.seg_taps[s];
+          const int kc = p.seg_kc[s];
+          for (int t = 0; t < taps; ++t) {
+            const int dy = (taps == 9) ? (t / 3 - 1) : 0;
+            const int dx = (taps == 9) ? (t % 3 - 1) : 0;
+            for (int c = 0; c < kc; ++c, ++kstep) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(kABytes + b_bytes));
+              tma_load_4d(ma, &full_bar[stage], sA + stage * kABytes, c * kBlockK, tc.w0 + dx, tc.h0 + dy, tc.n0);
+              tma_load_2d(&p.mapB, &full_bar[stage], sB + stage * b_bytes, kstep * kBlockK, tc.n_blk * p.BN);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kBlockM, static_cast<uint32_t>(p.BN), false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
+        for (int k = 0; k < p.ksteps; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_kmajor_sw128(sA_addr + stage * kABytes);
+          const uint64_t db = umma_desc_kmajor_sw128(sB_addr + stage * b_bytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (k | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int row = quarter * 32 + lane;
+    const int bwh = p.bw * p.bh;
+    const int r_w = row % p.bw;
+    const int r_h = (row / p.bw) % p.bh;
+    const int r_n = row / bwh;
+    const bool geglu = (p.act == UDT_ACT_GEGLU);
+    const int n_logical = geglu ? p.N_out / 2 : p.N_out;
+    const bool fast = (p.ldo % 8 == 0) && (p.residual == nullptr || p.ldr % 8 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int w = tc.w0 + r_w, h = tc.h0 + r_h, n = tc.n0 + r_n;
+      const bool valid = (w < p.W) && (h < p.H) && (n < p.NB);
+      const size_t m = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
+      if (geglu) {
+        const int half_bn = p.BN / 2;
+        for (int c0 = 0; c0 < half_bn; c0 += 32) {
+          uint32_t vx[32], vg[32];
+          tmem_ld32(taddr + c0, vx);
+          tmem_ld32(taddr + half_bn + c0, vg);
+          tmem_ld_wait();
+          const int col = tc.n_blk * half_bn + c0;      // logical output column
+          const int bcol = tc.n_blk * p.BN + c0;        // packed weight row of the x half
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(vx[j]);
+            float g = __uint_as_float(vg[j]);
+            if (p.bias != nullptr) {
+              x += __ldg(p.bias + bcol + j);
+              g += __ldg(p.bias + bcol + half_bn + j);
+            }
+            f[j] = x * gelu_erf_f(g);
+          }
+          if (valid && col < n_logical) {
+            __half* o = reinterpret_cast<__half*>(p.out) + m * p.ldo + col;
+            if (fast) {
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                uint4 ov;
+                ov.x = pack_half2(f[v * 8 + 0], f[v * 8 + 1]);
+                ov.y = pack_half2(f[v * 8 + 2], f[v * 8 + 3]);
+                ov.z = pack_half2(f[v * 8 + 4], f[v * 8 + 5]);
+                ov.w = pack_half2(f[v * 8 + 6], f[v * 8 + 7]);
+                o4[v] = ov;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) o[j] = __float2half_rn(f[j]);
+            }
+          }
+        }
+      } else if (p.BN >= 32) {
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          const int col = tc.n_blk * p.BN + c0;
+          if (valid && col < p.N_out) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            const int cnt = min(32, p.N_out - col);
+            finish_columns(p, f, cnt, m, n, col, fast);
+          }
+        }
+      } else {  // BN == 16
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        const int col = tc.n_blk * p.BN;
+        if (valid && col < p.N_out) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = (j < 16) ? __uint_as_float(v[j & 15]) : 0.0f;
+          const int cnt = min(16, p.N_out - col);
+          finish_columns(p, f, cnt, m, n, col, false);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+int pick_bn(int N_out, int tiles_m, int act, int sms) {
+  if (act == UDT_ACT_GEGLU) return kGegluTile;
+  if (N_out <= 16) return 16;
+  static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const int tn = (N_out + bn - 1) / bn;
+    const long tiles = static_cast<long>(tn) * tiles_m;
+    const long waves = (tiles + sms - 1) / sms;
+    // per-tile time ~ MMA time (prop. to BN, floor at 64 because the A tile read is smem-bound) + fixed overhead
+    const double per_tile = (bn < 64 ? 64 : bn) + 24.0;
+    const double cost = static_cast<double>(waves) * per_tile;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" int udt_geglu_tile(void) { return kGegluTile; }
+
+extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int32_t H, int32_t W, const void* weight,
+                         int32_t N_out, const float* bias, const float* rowbias, const void* residual, int32_t ldr,
+                         void* out, int32_t ldo, int32_t out_fp32, int32_t act, int32_t bn_hint, void* stream) {
+  using namespace udt_host;
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (nsrc < 1 || nsrc > 3) return fail(UDT_ERR_SHAPE, "udt_igemm: nsrc=%d (1..3)", nsrc);
+  if (NB < 1 || H < 1 || W < 1 || N_out < 1) return fail(UDT_ERR_SHAPE, "udt_igemm: bad shape NB=%d H=%d W=%d N=%d", NB, H, W, N_out);
+  if (act == UDT_ACT_GEGLU && (N_out % (2 * 32) != 0 || N_out % kGegluTile != 0 || out_fp32 || residual || rowbias))
+    return fail(UDT_ERR_SHAPE, "udt_igemm: GEGLU needs N_out %% %d == 0, fp16 out, no residual/rowbias", kGegluTile);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(udt_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(igemm smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+
+  IGemmParams p;
+  memset(&p, 0, sizeof(p));
+  // spatial tile: bw*bh*bn == 128, fewest tiles, prefer wide boxes
+  {
+    long best_tiles = -1;
+    for (int bw = 128; bw >= 1; bw >>= 1) {
+      for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+        const int bn = 128 / (bw * bh);
+        if (bw > 2 * W && bw > 1) continue;
+        const long t = static_cast<long>((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((NB + bn - 1) / bn);
+        if (best_tiles < 0 || t < best_tiles) {
+          best_tiles = t;
+          p.bw = bw;
+          p.bh = bh;
+          p.bn = bn;
+        }
+      }
+    }
+  }
+  p.W = W;
+  p.H = H;
+  p.NB = NB;
+  p.tiles_w = (W + p.bw - 1) / p.bw;
+  p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_nb = (NB + p.bn - 1) / p.bn;
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_nb;
+  const int sms = num_sms();
+  int BN = bn_hint > 0 ? bn_hint : pick_bn(N_out, tiles_m, act, sms);
+  if (BN != 16 && (BN % 32 != 0 || BN < 32 || BN > 256)) return fail(UDT_ERR_SHAPE, "udt_igemm: BN=%d unsupported", BN);
+  if (act == UDT_ACT_GEGLU && BN != kGegluTile) return fail(UDT_ERR_SHAPE, "udt_igemm: GEGLU requires BN=%d", kGegluTile);
+  p.BN = BN;
+  p.N_out = N_out;
+  p.tiles_n = (N_out + BN - 1) / BN;
+  p.num_tiles = tiles_m * p.tiles_n;
+
+  int ktotal = 0;
+  p.nseg = nsrc;
+  for (int s = 0; s < nsrc; ++s) {
+    const udt_gemm_src& a = srcs[s];
+    if (a.C < 64 || a.C % 64 != 0) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d has C=%d (multiple of 64 required)", s, a.C);
+    if (a.taps != 1 && a.taps != 9) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d taps=%d (1 or 9)", s, a.taps);
+    if (a.ld < a.C) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d ld=%d < C=%d", s, a.ld, a.C);
+    rc = make_tmap_nhwc(&p.mapA[s], a.ptr, a.C, W, H, NB, a.ld, p.bw, p.bh, p.bn);
+    if (rc != UDT_OK) return rc;
+    p.seg_kc[s] = a.C / 64;
+    p.seg_taps[s] = a.taps;
+    ktotal += a.taps * a.C;
+  }
+  p.ksteps = ktotal / 64;
+  rc = make_tmap_2d(&p.mapB, weight, static_cast<uint64_t>(ktotal), static_cast<uint64_t>(N_out),
+                    static_cast<uint64_t>(ktotal), 64, static_cast<uint32_t>(BN));
+  if (rc != UDT_OK) return rc;
+
+  const int stage_bytes = kABytes + BN * kBlockK * 2;
+  int stages = (kSmemBudget - kCtrlBytes - 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return fail(UDT_ERR_SHAPE, "udt_igemm: tile does not fit shared memory");
+  p.stages = stages;
+  p.bias = bias;
+  p.rowbias = rowbias;
+  p.residual = reinterpret_cast<const __half*>(residual);
+  p.ldr = ldr;
+  p.out = out;
+  p.ldo = ldo;
+  p.out_fp32 = out_fp32;
+  p.act = act;
+
+  const int smem = kCtrlBytes + 1024 + stages * stage_bytes;
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  udt_igemm_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("udt_igemm");
+}

@@ -1,0 +1,82 @@
+"""ctypes binding of libudt_b200.so (include/udt_api.h).
+
+The library is the only compute path of this package: if it is missing or the device is not sm_100 every call
+raises — there is no PyTorch / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libudt_b200.so")
+
+UDT_ACT_NONE, UDT_ACT_SILU, UDT_ACT_GEGLU = 0, 1, 2
+
+
+class UdtError(RuntimeError):
+    pass
+
+
+class GemmSrc(Structure):
+    """mirror of `udt_gemm_src`"""
+
+    _fields_ = [("ptr", c_void_p), ("C", c_int32), ("ld", c_int32), ("taps", c_int32)]
+
+
+# name -> (restype, argtypes): every symbol include/udt_api.h declares
+_PROTOTYPES = {
+    "udt_version": (c_int32, []),
+    "udt_arch": (c_int32, []),
+    "udt_last_error": (c_char_p, []),
+    "udt_num_sms": (c_int32, []),
+    "udt_geglu_tile": (c_int32, []),
+    "udt_igemm": (c_int32, [POINTER(GemmSrc), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
+                            c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "udt_groupnorm_nhwc": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                     c_void_p, c_float, c_int32, c_void_p, c_void_p]),
+    "udt_layernorm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p]),
+    "udt_fmha_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                               c_int32, c_int32, c_float, c_void_p]),
+    "udt_xattn_small_l": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                    c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "udt_softmax_rows": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "udt_cfg_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    "udt_cfg_euler_step": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p]),
+    "udt_upsample2x_nhwc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "udt_im2col3x3_nhwc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, c_void_p]),
+    "udt_nchw_f32_to_nhwc_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "udt_nhwc_to_nchw_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
+                                       c_int32, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library (built by `udifftext_b200.build`) and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UdtError(
+            f"{LIB_PATH} not found: run `python -m udifftext_b200.build` (or __graft_entry__.build()); "
+            "udifftext_b200 has no fallback compute path"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().udt_last_error()
+        raise UdtError(f"{what} failed with code {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,55 @@
+"""Weight repacking: reference `state_dict` layouts (conv OIHW fp32, Linear [out, in] fp32) -> the K-major fp16
+layouts udt_igemm consumes.  Pure tensor reshuffles, run once after checkpoint load (any device)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+GEGLU_TILE = 128  # must equal udt_geglu_tile()
+
+
+def pack_conv3x3(w_oihw: torch.Tensor, skip_1x1: Sequence[torch.Tensor] = ()) -> torch.Tensor:
+    """[O, I, 3, 3] -> fp16 [O, 9*I (+ sum of skip I)] with K ordered (tap = ky*3 + kx, channel); optional 1x1
+    skip-connection weights ([O, I_s, 1, 1] or [O, I_s]) are appended as extra K segments."""
+    o, i, kh, kw = w_oihw.shape
+    assert (kh, kw) == (3, 3)
+    parts = [w_oihw.permute(0, 2, 3, 1).reshape(o, 9 * i)]
+    for s in skip_1x1:
+        parts.append(s.reshape(o, -1))
+    return torch.cat(parts, dim=1).to(torch.float16).contiguous()
+
+
+def pack_conv3x3_padded(w_oihw: torch.Tensor, kpad: int) -> torch.Tensor:
+    """im2col variant: K = 9*I zero padded to `kpad` (multiple of 64)."""
+    o, i, _, _ = w_oihw.shape
+    out = torch.zeros((o, kpad), dtype=torch.float16, device=w_oihw.device)
+    out[:, : 9 * i] = w_oihw.permute(0, 2, 3, 1).reshape(o, 9 * i).to(torch.float16)
+    return out
+
+
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """[out, in] (or 1x1 conv [O, I, 1, 1]) -> fp16 [out, in]"""
+    return w.reshape(w.shape[0], -1).to(torch.float16).contiguous()
+
+
+def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """GEGLU projection [2*inner, in]: rows [0, inner) are x, [inner, 2*inner) the gate (attention.py:49-51).
+    Interleave per column tile of GEGLU_TILE: tile t = [x rows t*T/2 .. (t+1)*T/2 | gate rows ...]."""
+    two_inner, k = w.shape
+    inner = two_inner // 2
+    half = GEGLU_TILE // 2
+    assert inner % half == 0, f"GEGLU inner dim {inner} must be a multiple of {half}"
+    wx = w[:inner].reshape(inner // half, half, k)
+    wg = w[inner:].reshape(inner // half, half, k)
+    wp = torch.cat([wx, wg], dim=1).reshape(two_inner, k).to(torch.float16).contiguous()
+    bp = None
+    if b is not None:
+        bx = b[:inner].reshape(inner // half, half)
+        bg = b[inner:].reshape(inner // half, half)
+        bp = torch.cat([bx, bg], dim=1).reshape(two_inner).to(torch.float32).contiguous()
+    return wp, bp
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
