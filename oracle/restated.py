@@ -1,0 +1,362 @@
+"""CPU/GPU fp32 restatement of UDiffText's inference hot path in plain PyTorch — TEST INFRASTRUCTURE ONLY.
+
+This file is the parity oracle for the sm_100a kernels.  Only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s `cpu_baseline` / `--impl reference` legs may import it; the product (`udifftext_b200/`, `sgm/`)
+never does.  It restates, function by function, what the reference computes (file:line cites are relative to
+the reference repo root) as stateless functions over a reference-format `state_dict`, so that it can travel to
+the GPU box where `/root/reference` does not exist.
+
+Pinning: the reference ships no tests, golden vectors or fixtures for this path, so the
+oracle is pinned against the *unmodified reference modules imported in the build container*
+(`oracle/ref_import.py`): `oracle/make_golden.py` runs both on identical seeded weights/inputs, asserts
+agreement, and commits small golden vectors under `tests/golden/`.  Third-party arithmetic behind the
+reference (torch 2.1.1 / xformers 0.0.22 kernels) is not vendored; `memory_efficient_attention(q,k,v)` is
+restated as softmax(q k^T / sqrt(d)) v, its published definition.
+"""
+from __future__ import annotations
+
+import math
+import string
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+# --------------------------------------------------------------------------------------------- schedule
+
+
+def ddpm_variance_ratio(num: int = 1000, lo: float = 0.00085, hi: float = 0.0120) -> np.ndarray:
+    """(1 - abar_t) / abar_t in float64, betas linear in sqrt space (discretizer.py:41-56;
+    diffusionmodules/util.py:19-32).  Ascending in t."""
+    betas = torch.linspace(lo ** 0.5, hi ** 0.5, num, dtype=torch.float64) ** 2
+    abar = np.cumprod(1.0 - betas.numpy(), axis=0)
+    return (1 - abar) / abar
+
+
+def _sigmas_from_ratio(ratio: np.ndarray) -> torch.Tensor:
+    """the reference casts the float64 ratio to fp32 and takes the square root in fp32, then flips to
+    descending order (discretizer.py:66-68)"""
+    return torch.flip(torch.tensor(ratio, dtype=torch.float32) ** 0.5, (0,))
+
+
+def denoiser_sigmas(num_idx: int = 1000) -> torch.Tensor:
+    """DiscreteDenoiser.sigmas buffer: flip(descending) = ascending fp32 [num_idx] (denoiser.py:43-46 with
+    flip=True, do_append_zero=False; discretizer.py:16-20)."""
+    return torch.flip(_sigmas_from_ratio(ddpm_variance_ratio(num_idx)), (0,))
+
+
+def sampler_sigmas(n_steps: int, num: int = 1000) -> torch.Tensor:
+    """Descending sigma schedule with 0 appended, fp32 [n_steps+1] (discretizer.py:10-13,57-68;
+    sgm/util.py:188-189)."""
+    ratio = ddpm_variance_ratio(num)
+    if n_steps < num:
+        ts = np.linspace(num - 1, 0, n_steps, endpoint=False).astype(int)[::-1]
+        ratio = ratio[ts]
+    elif n_steps != num:
+        raise ValueError("more sampling steps than training timesteps")
+    sig = _sigmas_from_ratio(ratio)
+    return torch.cat([sig, sig.new_zeros(1)])
+
+
+def sigma_to_idx(sigma: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """nearest table entry (denoiser.py:49-51)"""
+    return (sigma[None, :] - table[:, None]).abs().argmin(dim=0)
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    """cat(cos, sin) sinusoid (diffusionmodules/util.py:206-230)"""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.device)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+# --------------------------------------------------------------------------------------------- UNet
+
+
+def _sub(sd: SD, prefix: str) -> SD:
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def _lin(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+def _gn(sd: SD, name: str, x: torch.Tensor, eps: float) -> torch.Tensor:
+    return F.group_norm(x, 32, sd[name + ".weight"], sd[name + ".bias"], eps)
+
+
+def _conv(sd: SD, name: str, x: torch.Tensor, stride: int = 1, padding: int = 1) -> torch.Tensor:
+    return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=padding)
+
+
+def _heads_split(t: torch.Tensor, heads: int) -> torch.Tensor:
+    b, n, c = t.shape
+    return t.reshape(b, n, heads, c // heads).permute(0, 2, 1, 3).reshape(b * heads, n, c // heads)
+
+
+def _heads_merge(t: torch.Tensor, heads: int) -> torch.Tensor:
+    bh, n, d = t.shape
+    return t.reshape(bh // heads, heads, n, d).permute(0, 2, 1, 3).reshape(bh // heads, n, heads * d)
+
+
+def res_block(sd: SD, p: str, x: torch.Tensor, emb: torch.Tensor) -> torch.Tensor:
+    """openaimodel.py:242-268 (no updown, no scale-shift): GN-SiLU-conv, + Linear(SiLU(emb)), GN-SiLU-conv, + skip"""
+    h = _conv(sd, p + "in_layers.2", F.silu(_gn(sd, p + "in_layers.0", x, 1e-5)))
+    h = h + _lin(sd, p + "emb_layers.1", F.silu(emb))[:, :, None, None]
+    h = _conv(sd, p + "out_layers.3", F.silu(_gn(sd, p + "out_layers.0", h, 1e-5)))
+    if p + "skip_connection.weight" in sd:
+        x = _conv(sd, p + "skip_connection", x, padding=0)
+    return x + h
+
+
+def self_attention(sd: SD, p: str, x: torch.Tensor, heads: int) -> torch.Tensor:
+    """attention.py:202-262 with context = x; xformers op restated as softmax(q k^T d^-1/2) v"""
+    q, k, v = (_heads_split(_lin(sd, p + n, x), heads) for n in ("to_q", "to_k", "to_v"))
+    o = F.scaled_dot_product_attention(q, k, v)
+    return _lin(sd, p + "to_out.0", _heads_merge(o, heads))
+
+
+def text_cross_attention(sd: SD, p: str, x: torch.Tensor, ctx: torch.Tensor, heads: int,
+                         probs_out: Optional[list] = None) -> torch.Tensor:
+    """attention.py:140-174: einsum scores * d^-1/2, softmax over tokens (sigmoid if one token), probs cached"""
+    q = _heads_split(_lin(sd, p + "to_q", x), heads)
+    k = _heads_split(_lin(sd, p + "to_k", ctx), heads)
+    v = _heads_split(_lin(sd, p + "to_v", ctx), heads)
+    sim = torch.einsum("bid,bjd->bij", q, k) * (q.shape[-1] ** -0.5)
+    sim = sim.softmax(dim=-1) if sim.shape[-1] > 1 else sim.sigmoid()
+    if probs_out is not None:
+        probs_out.append(sim)
+    o = torch.einsum("bij,bjd->bid", sim, v)
+    return _lin(sd, p + "to_out.0", _heads_merge(o, heads))
+
+
+def spatial_transformer(sd: SD, p: str, x: torch.Tensor, ctx: torch.Tensor, head_dim: int,
+                        probs_out: Optional[list] = None) -> torch.Tensor:
+    """attention.py:398-416 (use_linear) around one BasicTransformerBlock (attention.py:314-341)"""
+    b, c, hh, ww = x.shape
+    heads = c // head_dim
+    t = _gn(sd, p + "norm", x, 1e-6).permute(0, 2, 3, 1).reshape(b, hh * ww, c)
+    t = _lin(sd, p + "proj_in", t)
+    depth = 0
+    while p + f"transformer_blocks.{depth}.norm1.weight" in sd:
+        q = p + f"transformer_blocks.{depth}."
+        ln = lambda name, u: F.layer_norm(u, (c,), sd[q + name + ".weight"], sd[q + name + ".bias"], 1e-5)
+        t = self_attention(sd, q + "attn1.", ln("norm1", t), heads) + t
+        if q + "t_attn.to_q.weight" in sd:
+            t = text_cross_attention(sd, q + "t_attn.", ln("t_norm", t), ctx, heads, probs_out) + t
+        g = _lin(sd, q + "ff.net.0.proj", ln("norm3", t))
+        a, gate = g.chunk(2, dim=-1)
+        t = _lin(sd, q + "ff.net.2", a * F.gelu(gate)) + t
+        depth += 1
+    t = _lin(sd, p + "proj_out", t)
+    return t.reshape(b, hh, ww, c).permute(0, 3, 1, 2) + x
+
+
+def _run_block(sd: SD, p: str, h: torch.Tensor, emb: torch.Tensor, ctx: torch.Tensor, head_dim: int,
+               probs_out: Optional[list]) -> torch.Tensor:
+    """TimestepEmbedSequential dispatch (openaimodel.py:43-63), layer kinds inferred from the key names"""
+    j = 0
+    while True:
+        q = f"{p}{j}."
+        if q + "in_layers.0.weight" in sd:
+            h = res_block(sd, q, h, emb)
+        elif q + "proj_in.weight" in sd:
+            h = spatial_transformer(sd, q, h, ctx, head_dim, probs_out)
+        elif q + "op.weight" in sd:  # Downsample: conv3x3 stride 2 pad 1 (openaimodel.py:132-139)
+            h = _conv(sd, q + "op", h, stride=2)
+        elif q + "conv.weight" in sd:  # Upsample: nearest x2 then conv3x3 (openaimodel.py:99-102)
+            h = _conv(sd, q + "conv", F.interpolate(h, scale_factor=2, mode="nearest"))
+        elif q + "weight" in sd:  # plain conv (input_blocks.0.0)
+            h = _conv(sd, q[:-1], h)
+        else:
+            return h
+        j += 1
+
+
+def unet_forward(sd: SD, x: torch.Tensor, timesteps: torch.Tensor, t_context: torch.Tensor, model_channels: int = 320,
+                 head_dim: int = 64, probs_out: Optional[list] = None) -> torch.Tensor:
+    """UnifiedUNetModel.forward (openaimodel.py:593-624); `sd` keys are relative to `model.diffusion_model.`"""
+    emb = timestep_embedding(timesteps, model_channels)
+    emb = _lin(sd, "time_embed.2", F.silu(_lin(sd, "time_embed.0", emb)))
+    hs: List[torch.Tensor] = []
+    h = x
+    i = 0
+    while f"input_blocks.{i}.0.weight" in sd or f"input_blocks.{i}.0.in_layers.0.weight" in sd or f"input_blocks.{i}.0.op.weight" in sd:
+        h = _run_block(sd, f"input_blocks.{i}.", h, emb, t_context, head_dim, probs_out)
+        hs.append(h)
+        i += 1
+    h = _run_block(sd, "middle_block.", h, emb, t_context, head_dim, probs_out)
+    i = 0
+    while f"output_blocks.{i}.0.in_layers.0.weight" in sd:
+        h = torch.cat([h, hs.pop()], dim=1)
+        h = _run_block(sd, f"output_blocks.{i}.", h, emb, t_context, head_dim, probs_out)
+        i += 1
+    return _conv(sd, "out.2", F.silu(_gn(sd, "out.0", h, 1e-5)))
+
+
+# --------------------------------------------------------------------------------------------- VAE
+
+
+def _vae_res(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    """model.py:128-148 with temb=None; eps 1e-6 norms (model.py:49-52)"""
+    h = _conv(sd, p + "conv1", F.silu(_gn(sd, p + "norm1", x, 1e-6)))
+    h = _conv(sd, p + "conv2", F.silu(_gn(sd, p + "norm2", h, 1e-6)))
+    if p + "nin_shortcut.weight" in sd:
+        x = _conv(sd, p + "nin_shortcut", x, padding=0)
+    return x + h
+
+
+def _vae_attn(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    """single-head attention over pixels (model.py:228-262), scale C^-1/2"""
+    b, c, hh, ww = x.shape
+    hn = _gn(sd, p + "norm", x, 1e-6)
+    q, k, v = (_conv(sd, p + n, hn, padding=0).reshape(b, c, hh * ww).permute(0, 2, 1) for n in ("q", "k", "v"))
+    o = F.scaled_dot_product_attention(q, k, v)
+    o = o.permute(0, 2, 1).reshape(b, c, hh, ww)
+    return x + _conv(sd, p + "proj_out", o, padding=0)
+
+
+def vae_encode_moments(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """Encoder.forward + quant_conv (model.py:571-596; autoencoder.py:304-309); `sd` relative to the AE root"""
+    h = _conv(sd, "encoder.conv_in", x)
+    lvl = 0
+    while f"encoder.down.{lvl}.block.0.norm1.weight" in sd:
+        blk = 0
+        while f"encoder.down.{lvl}.block.{blk}.norm1.weight" in sd:
+            h = _vae_res(sd, f"encoder.down.{lvl}.block.{blk}.", h)
+            blk += 1
+        if f"encoder.down.{lvl}.downsample.conv.weight" in sd:  # pad right/bottom, stride 2 (model.py:77-85)
+            h = _conv(sd, f"encoder.down.{lvl}.downsample.conv", F.pad(h, (0, 1, 0, 1)), stride=2, padding=0)
+        lvl += 1
+    h = _vae_res(sd, "encoder.mid.block_1.", h)
+    h = _vae_attn(sd, "encoder.mid.attn_1.", h)
+    h = _vae_res(sd, "encoder.mid.block_2.", h)
+    h = _conv(sd, "encoder.conv_out", F.silu(_gn(sd, "encoder.norm_out", h, 1e-6)))
+    return _conv(sd, "quant_conv", h, padding=0)
+
+
+def posterior_sample(moments: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """DiagonalGaussianDistribution.sample (distributions.py:24-41)"""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+
+
+def vae_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
+    """post_quant_conv + Decoder.forward (autoencoder.py:313-316; model.py:710-743)"""
+    h = _conv(sd, "decoder.conv_in", _conv(sd, "post_quant_conv", z, padding=0))
+    h = _vae_res(sd, "decoder.mid.block_1.", h)
+    h = _vae_attn(sd, "decoder.mid.attn_1.", h)
+    h = _vae_res(sd, "decoder.mid.block_2.", h)
+    levels = 0
+    while f"decoder.up.{levels}.block.0.norm1.weight" in sd:
+        levels += 1
+    for lvl in reversed(range(levels)):
+        blk = 0
+        while f"decoder.up.{lvl}.block.{blk}.norm1.weight" in sd:
+            h = _vae_res(sd, f"decoder.up.{lvl}.block.{blk}.", h)
+            blk += 1
+        if f"decoder.up.{lvl}.upsample.conv.weight" in sd:
+            h = _conv(sd, f"decoder.up.{lvl}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"))
+    return _conv(sd, "decoder.conv_out", F.silu(_gn(sd, "decoder.norm_out", h, 1e-6)))
+
+
+# --------------------------------------------------------------------------------------------- conditioner
+
+CHARSET = string.printable[:-6]  # encoders/modules.py:1097
+
+
+def label_indices(labels: Sequence[str], max_len: int = 12) -> torch.Tensor:
+    """char -> 1..94, unknown / pad -> 0 (encoders/modules.py:1149-1158)"""
+    rows = []
+    for lab in labels:
+        assert len(lab) <= max_len
+        rows.append([CHARSET.find(ch) + 1 for ch in lab] + [0] * (max_len - len(lab)))
+    return torch.tensor(rows, dtype=torch.long)
+
+
+def label_encoder(sd: SD, labels: Sequence[str], n_heads: int = 8, max_len: int = 12) -> torch.Tensor:
+    """Embedding + sinusoid PE + post-LN TransformerEncoder (ReLU, no mask) (encoders/modules.py:1160-1173)"""
+    idx = label_indices(labels, max_len).to(sd["label_embedding.weight"].device)
+    x = sd["label_embedding.weight"][idx] + sd["pos_embedding.pe"][None]
+    d = x.shape[-1]
+    layer = 0
+    while f"encoder.layers.{layer}.linear1.weight" in sd:
+        p = f"encoder.layers.{layer}."
+        qkv = F.linear(x, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"])
+        q, k, v = (_heads_split(t, n_heads) for t in qkv.chunk(3, dim=-1))
+        a = _heads_merge(F.scaled_dot_product_attention(q, k, v), n_heads)
+        a = F.linear(a, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+        x = F.layer_norm(x + a, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+        f = _lin(sd, p + "linear2", F.relu(_lin(sd, p + "linear1", x)))
+        x = F.layer_norm(x + f, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+        layer += 1
+    return x
+
+
+def conditioner(sd: SD, batch: dict, noise_c: torch.Tensor, noise_uc: torch.Tensor, scale_factor: float = 0.18215
+                ) -> Tuple[dict, dict]:
+    """GeneralConditioner.get_unconditional_conditioning with force_uc_zero_embeddings=["label"]
+    (encoders/modules.py:154-217): c and uc dicts {t_crossattn [B,12,2048], concat [B,5,h,w]}.
+    `sd` is relative to `conditioner.`; `noise_c` / `noise_uc` are the two posterior draws (RNG draws #1, #2)."""
+    emb = label_encoder(_sub(sd, "embedders.0."), batch["label"])
+    mask8 = F.interpolate(batch["mask"], scale_factor=0.125, mode="bilinear")  # SpatialRescaler :843-857
+    moments = vae_encode_moments(_sub(sd, "embedders.2.model."), batch["masked"])  # LatentEncoder :1011-1014
+    c = {"t_crossattn": emb, "concat": torch.cat([mask8, scale_factor * posterior_sample(moments, noise_c)], dim=1)}
+    uc = {"t_crossattn": torch.zeros_like(emb),
+          "concat": torch.cat([mask8, scale_factor * posterior_sample(moments, noise_uc)], dim=1)}
+    return c, uc
+
+
+# --------------------------------------------------------------------------------------------- sampler
+
+
+def cfg_denoise_eps(unet_sd: SD, x: torch.Tensor, sigma: float, table: torch.Tensor, c: dict, uc: dict, scale: float,
+                    probs_out: Optional[list] = None) -> torch.Tensor:
+    """One CFG-doubled UNet evaluation, returned as the guided eps (guiders.py:25-40; denoiser.py:22-28;
+    denoiser_scaling.py:16-22; wrappers.py:27; sampling_utils.py:7-9,39-40)."""
+    b = x.shape[0]
+    sig = torch.full((2 * b,), float(sigma), dtype=torch.float32, device=x.device)
+    idx = sigma_to_idx(sig, table.to(x.device))
+    sig_q = table.to(x.device)[idx]
+    c_in = 1.0 / (sig_q ** 2 + 1.0) ** 0.5
+    xin = torch.cat([x, x]) * c_in[:, None, None, None]
+    net_in = torch.cat([xin, torch.cat([uc["concat"], c["concat"]])], dim=1)
+    ctx = torch.cat([uc["t_crossattn"], c["t_crossattn"]])
+    out = unet_forward(unet_sd, net_in, idx, ctx, probs_out=probs_out)
+    denoised = out * (-sig_q)[:, None, None, None] + torch.cat([x, x])
+    d_u, d_c = denoised.chunk(2)
+    den = d_u + scale * (d_c - d_u)
+    return (x - den) / float(sigma)
+
+
+def euler_sample(unet_sd: SD, noise: torch.Tensor, c: dict, uc: dict, n_steps: int, scale: float,
+                 trace: Optional[list] = None) -> torch.Tensor:
+    """EulerEDMSampler.__call__ with s_churn = 0 (sampling.py:48-59,324-353,355-420)"""
+    sig = sampler_sigmas(n_steps)
+    table = denoiser_sigmas()
+    x = noise * torch.sqrt(1.0 + sig[0] ** 2.0)
+    for i in range(n_steps):
+        eps = cfg_denoise_eps(unet_sd, x, float(sig[i]), table, c, uc, scale)
+        if trace is not None:
+            trace.append(eps.clone())
+        x = x + (sig[i + 1] - sig[i]) * eps
+    return x
+
+
+def predict(sd: SD, batch: dict, n_steps: int, scale: float, scale_factor: float = 0.18215) -> Tuple[torch.Tensor, torch.Tensor]:
+    """test.py:19-40 with noise_iters = 0: RNG draws in reference order (posterior c, posterior uc, init noise)."""
+    b, _, hh, ww = batch["image"].shape
+    lat = (b, 4, hh // 8, ww // 8)
+    dev = batch["image"].device
+    noise_c = torch.randn(lat).to(dev)
+    noise_uc = torch.randn(lat).to(dev)
+    c, uc = conditioner(_sub(sd, "conditioner."), batch, noise_c, noise_uc, scale_factor)
+    x = torch.randn(lat).to(dev)
+    z = euler_sample(_sub(sd, "model.diffusion_model."), x, c, uc, n_steps, scale)
+    img = vae_decode(_sub(sd, "first_stage_model."), z / scale_factor)
+    return torch.clamp((img + 1.0) / 2.0, 0.0, 1.0), z

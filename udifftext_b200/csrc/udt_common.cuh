@@ -12,7 +12,7 @@
 #ifndef UDT_SPIN_LIMIT
 // Upper bound on mbarrier spin iterations before the kernel traps instead of hanging the GPU.
 // (each failed try_wait suspends for up to ~1 us, so this is seconds of wall clock)
-#define UDT_SPIN_LIMIT (1u << 24)
+#define UDT_SPIN_LIMIT (1u << 22)
 #endif
 
 namespace udt {
