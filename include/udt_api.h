@@ -54,10 +54,10 @@ typedef struct {
  * as `rowbias`, residual adds (openaimodel.py:268; attention.py:315-341,416) and GEGLU (attention.py:49-51).
  * `weight` is fp16 [N_out, K_total], K ordered (segment, tap = ky*3+kx, channel).  For UDT_ACT_GEGLU the
  * logical output has N_out/2 columns (see udt_geglu_tile()).  `residual` may alias `out`.
- * `bn_hint` = 0 lets the library pick the column tile. */
+ * `rowbias` is fp32 [NB, ld_rowbias] (one row per image).  `bn_hint` = 0 lets the library pick the column tile. */
 int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int32_t H, int32_t W, const void* weight,
-              int32_t N_out, const float* bias, const float* rowbias, const void* residual, int32_t ldr, void* out,
-              int32_t ldo, int32_t out_fp32, int32_t act, int32_t bn_hint, void* stream);
+              int32_t N_out, const float* bias, const float* rowbias, int32_t ld_rowbias, const void* residual,
+              int32_t ldr, void* out, int32_t ldo, int32_t out_fp32, int32_t act, int32_t bn_hint, void* stream);
 /* column tile (BN) the GEGLU weight interleave must be packed for (x half then gate half per tile) */
 int udt_geglu_tile(void);
 
@@ -65,7 +65,9 @@ int udt_geglu_tile(void);
  * concatenation of two tensors (`x1` may be NULL) and writes one [NB, HW, C0+C1] tensor.
  * Replaces GroupNorm32+SiLU (diffusionmodules/util.py:273-275; openaimodel.py:185,220,538), Normalize
  * (attention.py:82-85; model.py:49-52) and the th.cat of skip connections (openaimodel.py:620).
- * `stats_ws` is a caller-owned, 8-byte aligned workspace of 16*NB*groups bytes (fp64 sum / sum of squares). */
+ * Deterministic (no atomics): per-CTA fp64 partial sums are written to `stats_ws`, a caller-owned 8-byte
+ * aligned workspace of udt_groupnorm_ws_bytes(NB, HW, C0+C1, groups) bytes, and folded in a fixed order. */
+int64_t udt_groupnorm_ws_bytes(int32_t NB, int32_t HW, int32_t C, int32_t groups);
 int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, int32_t C1, void* y, int32_t NB, int32_t HW,
                        int32_t groups, const float* gamma, const float* beta, float eps, int32_t silu,
                        void* stats_ws, void* stream);

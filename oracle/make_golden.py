@@ -1,0 +1,137 @@
+"""Container-only generator of the committed golden vectors (tests/golden/*.pt) — TEST INFRASTRUCTURE.
+
+Runs the UNMODIFIED reference (imported from /root/reference with the shims of oracle/ref_import.py) on the
+seeded synthetic weights / batches of udifftext_b200.synth, checks that oracle/restated.py reproduces it, and
+stores the reference's outputs.  The GPU box cannot see the reference; its tests compare the CUDA path with
+these vectors and with the restatement.
+
+One deliberate deviation, documented in DESIGN.md: the reference leaves its LabelEncoder in *training* mode at
+inference (`embedder.train = disabled_train` is installed before `model.eval()`, encoders/modules.py:117-119,
+util.py:18-20), so dropout(p=0.1) makes the text embedding random.  Golden vectors are generated with the
+LabelEncoder switched to eval mode (`nn.Module.train(le, False)`) — the deterministic function both sides share.
+
+usage: python oracle/make_golden.py [tiny] [full_unet] [c1]
+"""
+import os
+import sys
+import time
+
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import, restated as R  # noqa: E402
+from oracle.make_manifest import small_overrides  # noqa: E402
+from udifftext_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SAMPLER_CFG = dict(
+    discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"},
+    s_churn=0.0, s_tmin=0.0, s_tmax=999.0, s_noise=1.0, verbose=False, device="cpu")
+
+
+def reference_engine(name: str, seed: int = 1234):
+    m = ref_import.build_reference_engine(seed, small_overrides(name))
+    sd = synth.synthetic_state_dict(synth.load_manifest(name), seed)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    nn.Module.train(m.conditioner.embedders[0], False)  # see module docstring
+    return m, sd
+
+
+def reference_predict(m, batch, steps, scale, seed):
+    """test.py:19-40 on CPU (the script hard-codes cuda; same calls, same RNG order, noise_iters = 0)."""
+    from sgm.modules.diffusionmodules.sampling import EulerEDMSampler
+    sampler = EulerEDMSampler(num_steps=steps, guider_config={
+        "target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": scale}}, **SAMPLER_CFG)
+    batch_uc = dict(batch)
+    batch_uc["txt"] = ["" for _ in batch["txt"]]
+    batch_uc["label"] = ["" for _ in batch["label"]]
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        c, uc = m.conditioner.get_unconditional_conditioning(batch, batch_uc=batch_uc, force_uc_zero_embeddings=["label"])
+        b, _, hh, ww = batch["image"].shape
+        x = torch.randn((b, 4, hh // 8, ww // 8))
+        z = sampler(m, x, cond=c, batch=batch, uc=uc, init_step=0, aae_enabled=False, detailed=False)
+        img = torch.clamp((m.decode_first_stage(z) + 1.0) / 2.0, 0.0, 1.0)
+    return img, z, c, uc
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def gen_tiny():
+    m, sd = reference_engine("tiny")
+    a = synth.ARCH["tiny"]
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((4, 9, 8, 8), generator=g)
+    t = torch.tensor([999, 500, 20, 3])
+    ctx = torch.randn((4, 12, a["unet"]["t_context_dim"]), generator=g)
+    with torch.no_grad():
+        ref = m.model.diffusion_model(x, timesteps=t, t_context=ctx)
+        probs = [it["attn_map"].clone() for it in m.model.diffusion_model.attn_map_cache]
+        mine_probs = []
+        mine = R.unet_forward(R._sub(sd, "model.diffusion_model."), x, t, ctx, model_channels=a["unet"]["model_channels"],
+                              probs_out=mine_probs)
+    assert rel(mine, ref) < 1e-5, rel(mine, ref)
+    assert max((p - q).abs().max().item() for p, q in zip(probs, mine_probs)) < 1e-5
+    batch = synth.synthetic_batch(101, 2, 64, 64, None)
+    img, z, c, uc = reference_predict(m, batch, 4, 5.0, 1101)
+    torch.manual_seed(1101)
+    with torch.no_grad():
+        img2, z2 = R.predict(sd, batch, 4, 5.0)
+    print("tiny: unet rel", rel(mine, ref), "predict z rel", rel(z2, z), "pixels rel", rel(img2, img), "eps rms",
+          ref.pow(2).mean().sqrt().item(), "pixel mean", img.mean().item(), "sat frac",
+          ((img == 0) | (img == 1)).float().mean().item())
+    assert rel(z2, z) < 1e-4 and rel(img2, img) < 1e-4
+    torch.save({"unet_x": x, "unet_t": t, "unet_ctx": ctx, "unet_out": ref, "unet_probs": probs,
+                "predict_config_id": 101, "predict_seed": 1101, "predict_steps": 4, "predict_scale": 5.0,
+                "predict_pixels": img, "predict_z": z, "c_concat": c["concat"], "uc_concat": uc["concat"],
+                "c_crossattn": c["t_crossattn"]}, os.path.join(GOLD, "tiny.pt"))
+
+
+def gen_full_unet():
+    m, sd = reference_engine("full")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((2, 9, 64, 64), generator=g)
+    t = torch.tensor([999, 19])
+    ctx = torch.randn((2, 12, 2048), generator=g)
+    t0 = time.time()
+    with torch.no_grad():
+        ref = m.model.diffusion_model(x, timesteps=t, t_context=ctx)
+        dt = time.time() - t0
+        probs6 = [it["attn_map"][:, ::64].clone() for it in m.model.diffusion_model.attn_map_cache]
+        mine = R.unet_forward(R._sub(sd, "model.diffusion_model."), x, t, ctx)
+    print("full unet: rel", rel(mine, ref), "eps rms", ref.pow(2).mean().sqrt().item(), "ref seconds", dt)
+    assert rel(mine, ref) < 1e-5
+    torch.save({"x": x, "t": t, "ctx": ctx, "out": ref, "probs_strided64": probs6, "cpu_seconds_batch2": dt,
+                "threads": torch.get_num_threads()}, os.path.join(GOLD, "full_unet.pt"))
+    return m, sd
+
+
+def gen_c1(m=None, sd=None):
+    """BASELINE.json configs[0]: 1x512x512, 4-char string, 10 steps, reference PyTorch CPU fp32."""
+    if m is None:
+        m, sd = reference_engine("full")
+    batch = synth.synthetic_batch(1, 1, 512, 512, 4)
+    t0 = time.time()
+    img, z, c, uc = reference_predict(m, batch, 10, 5.0, 1001)
+    dt = time.time() - t0
+    print("c1: reference predict seconds", dt, "pixel mean", img.mean().item(), "sat frac",
+          ((img == 0) | (img == 1)).float().mean().item(), "z rms", z.pow(2).mean().sqrt().item())
+    torch.save({"config_id": 1, "seed": 1001, "steps": 10, "scale": 5.0, "pixels_f16": img.half(), "z": z,
+                "c_concat": c["concat"], "uc_concat": uc["concat"], "c_crossattn": c["t_crossattn"],
+                "cpu_seconds": dt, "threads": torch.get_num_threads()}, os.path.join(GOLD, "c1.pt"))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["tiny"]
+    os.makedirs(GOLD, exist_ok=True)
+    if "tiny" in what:
+        gen_tiny()
+    m = sd = None
+    if "full_unet" in what:
+        m, sd = gen_full_unet()
+    if "c1" in what:
+        gen_c1(m, sd)

@@ -178,9 +178,11 @@ def _run_block(sd: SD, p: str, h: torch.Tensor, emb: torch.Tensor, ctx: torch.Te
         j += 1
 
 
-def unet_forward(sd: SD, x: torch.Tensor, timesteps: torch.Tensor, t_context: torch.Tensor, model_channels: int = 320,
-                 head_dim: int = 64, probs_out: Optional[list] = None) -> torch.Tensor:
+def unet_forward(sd: SD, x: torch.Tensor, timesteps: torch.Tensor, t_context: torch.Tensor,
+                 model_channels: Optional[int] = None, head_dim: int = 64, probs_out: Optional[list] = None) -> torch.Tensor:
     """UnifiedUNetModel.forward (openaimodel.py:593-624); `sd` keys are relative to `model.diffusion_model.`"""
+    if model_channels is None:
+        model_channels = sd["time_embed.0.weight"].shape[1]
     emb = timestep_embedding(timesteps, model_channels)
     emb = _lin(sd, "time_embed.2", F.silu(_lin(sd, "time_embed.0", emb)))
     hs: List[torch.Tensor] = []

@@ -57,7 +57,7 @@ def main():
         g = torch.ones(c, device=dev)
         b = torch.zeros(c, device=dev)
         y = torch.empty_like(x)
-        ws = torch.empty(2 * nb * 32, device=dev, dtype=torch.float64)
+        ws = torch.empty(ops.groupnorm_ws_bytes(nb, hw, c) // 8, device=dev, dtype=torch.float64)
         ms = timeit(lambda: ops.groupnorm(x, g, b, 1e-5, True, out=y, ws=ws))
         out.append({"op": "groupnorm_silu", "nb": nb, "hw": hw, "c": c, "ms": round(ms, 4), "gbs": round(4.0 * x.numel() / ms / 1e6, 1)})
         ms = timeit(lambda: ops.layernorm(x, g, b, 1e-5, out=y))

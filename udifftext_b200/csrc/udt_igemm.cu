@@ -44,7 +44,7 @@ struct IGemmParams {
   const float* bias;
   const float* rowbias;
   const __half* residual;
-  int32_t ldr;
+  int32_t ldr, ld_rowbias;
   void* out;
   int32_t ldo, out_fp32, act;
 };
@@ -76,7 +76,7 @@ __device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[
       if (j < cnt) f[j] += __ldg(p.bias + col + j);
   }
   if (p.rowbias != nullptr) {
-    const float* rb = p.rowbias + static_cast<size_t>(img) * p.N_out + col;
+    const float* rb = p.rowbias + static_cast<size_t>(img) * p.ld_rowbias + col;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < cnt) f[j] += __ldg(rb + j);
@@ -362,8 +362,9 @@ int pick_bn(int N_out, int tiles_m, int act, int sms) {
 extern "C" int udt_geglu_tile(void) { return kGegluTile; }
 
 extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int32_t H, int32_t W, const void* weight,
-                         int32_t N_out, const float* bias, const float* rowbias, const void* residual, int32_t ldr,
-                         void* out, int32_t ldo, int32_t out_fp32, int32_t act, int32_t bn_hint, void* stream) {
+                         int32_t N_out, const float* bias, const float* rowbias, int32_t ld_rowbias, const void* residual,
+                         int32_t ldr, void* out, int32_t ldo, int32_t out_fp32, int32_t act, int32_t bn_hint,
+                         void* stream) {
   using namespace udt_host;
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
@@ -439,6 +440,7 @@ extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int
   p.stages = stages;
   p.bias = bias;
   p.rowbias = rowbias;
+  p.ld_rowbias = ld_rowbias;
   p.residual = reinterpret_cast<const __half*>(residual);
   p.ldr = ldr;
   p.out = out;

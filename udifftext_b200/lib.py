@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libudt_b200.so")
@@ -33,7 +33,8 @@ _PROTOTYPES = {
     "udt_num_sms": (c_int32, []),
     "udt_geglu_tile": (c_int32, []),
     "udt_igemm": (c_int32, [POINTER(GemmSrc), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
-                            c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+                            c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "udt_groupnorm_ws_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "udt_groupnorm_nhwc": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                      c_void_p, c_float, c_int32, c_void_p, c_void_p]),
     "udt_layernorm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p]),

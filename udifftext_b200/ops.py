@@ -39,6 +39,7 @@ def igemm(
     rowbias: Optional[torch.Tensor] = None,
     residual: Optional[torch.Tensor] = None,
     ldr: int = 0,
+    ld_rowbias: int = 0,
     out_fp32: bool = False,
     act: int = UDT_ACT_NONE,
     bn_hint: int = 0,
@@ -51,7 +52,8 @@ def igemm(
         arr[i].C = c
         arr[i].ld = ld
         arr[i].taps = taps
-    rc = L.udt_igemm(arr, len(srcs), nb, h, w, weight.data_ptr(), n_out, _ptr(bias), _ptr(rowbias), _ptr(residual), ldr,
+    rc = L.udt_igemm(arr, len(srcs), nb, h, w, weight.data_ptr(), n_out, _ptr(bias), _ptr(rowbias),
+                     (ld_rowbias or n_out) if rowbias is not None else 0, _ptr(residual), ldr,
                      out.data_ptr(), ldo, int(out_fp32), act, bn_hint, _stream())
     _lib.check(rc, "udt_igemm")
     return out
@@ -82,7 +84,12 @@ def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] 
         out = torch.empty((nb, h, w, n), device=x.device, dtype=torch.float32 if out_fp32 else torch.float16)
     srcs = [(x, c, c, 9)] + [(s, s.shape[-1], s.shape[-1], 1) for s in skip_srcs]
     return igemm(srcs, nb, h, w, weight, n, out, n, bias=bias, rowbias=rowbias, residual=residual,
-                 ldr=0 if residual is None else residual.shape[-1], out_fp32=out_fp32, bn_hint=bn_hint)
+                 ldr=0 if residual is None else residual.shape[-1], out_fp32=out_fp32, bn_hint=bn_hint,
+                 ld_rowbias=0 if rowbias is None else rowbias.stride(0))
+
+
+def groupnorm_ws_bytes(nb: int, hw: int, c: int, groups: int = 32) -> int:
+    return int(_lib.load().udt_groupnorm_ws_bytes(nb, hw, c, groups))
 
 
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
@@ -96,8 +103,8 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     hw = x0.numel() // (nb * c0)
     if out is None:
         out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.float16)
-    if ws is None:
-        ws = torch.empty(2 * nb * groups, device=x0.device, dtype=torch.float64)
+    if ws is None or ws.numel() * 8 < groupnorm_ws_bytes(nb, hw, c0 + c1, groups):
+        ws = torch.empty(groupnorm_ws_bytes(nb, hw, c0 + c1, groups) // 8, device=x0.device, dtype=torch.float64)
     rc = L.udt_groupnorm_nhwc(x0.data_ptr(), c0, _ptr(x1), c1, out.data_ptr(), nb, hw, groups, gamma.data_ptr(),
                               beta.data_ptr(), float(eps), int(silu), ws.data_ptr(), _stream())
     _lib.check(rc, "udt_groupnorm_nhwc")
