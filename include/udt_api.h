@@ -30,6 +30,7 @@ extern "C" {
 #define UDT_ACT_NONE 0
 #define UDT_ACT_SILU 1
 #define UDT_ACT_GEGLU 2 /* out[:, j] = x_j * gelu_erf(gate_j); weight rows interleaved per column tile */
+#define UDT_ACT_RELU 3
 
 int udt_version(void);            /* ABI version (1) */
 int udt_arch(void);               /* compute capability of the current device *10 (100 on B200); <0 on error */
@@ -37,27 +38,47 @@ const char* udt_last_error(void); /* thread-local message of the last failing ca
 int udt_num_sms(void);
 
 /* One K-segment of the implicit GEMM: an NHWC fp16 activation tensor read either point-wise (taps = 1:
- * nn.Linear / 1x1 conv) or through a 3x3, stride-1, zero-pad-1 window (taps = 9). */
+ * nn.Linear / 1x1 conv) or through a 3x3 window (taps = 9) with zero padding, stride 1 or 2. */
 typedef struct {
   const void* ptr; /* fp16 [NB, H, W, ld] */
-  int32_t C;       /* channels consumed from this tensor (multiple of 64) */
+  int32_t C;       /* channels consumed from this tensor (multiple of 8; each tap is zero-filled up to a multiple
+                      of 64 by TMA, and the packed weight carries the same per-tap padding) */
   int32_t ld;      /* channel pitch in elements (>= C, multiple of 8) */
   int32_t taps;    /* 1 or 9 */
+  int32_t H, W;    /* spatial size of this tensor; 0 = output size * stride */
+  int32_t stride;  /* 1 or 2 (0 = 1): output pixel (y, x) reads input pixel (y*stride + ky - pad, ...) */
+  int32_t pad;     /* low-side zero padding of the 3x3 window: 1 = symmetric pad 1 (openaimodel.py:132-139),
+                      0 = the VAE's pad-(0,1,0,1) downsample (model.py:77-85) */
 } udt_gemm_src;
 
+typedef struct {
+  udt_gemm_src src[3];
+  int32_t nsrc;          /* 1..3 K-segments */
+  int32_t NB, H, W;      /* output pixels: M = NB*H*W rows (a plain GEMM is NB = H = 1, W = M) */
+  const void* weight;    /* fp16 [N_out, ldw], K ordered (segment, tap = ky*3+kx, channel padded to 64) */
+  int32_t ldw;           /* weight row pitch in elements (0 = K_total) */
+  int32_t N_out;
+  const float* bias;     /* fp32 [N_out] or NULL */
+  const float* rowbias;  /* fp32 [NB, ld_rowbias] (one row per image; ld_rowbias = 0 broadcasts one row) or NULL */
+  int32_t ld_rowbias;
+  const void* residual;  /* fp16 [M, ldr] or NULL; may alias out */
+  int32_t ldr;
+  void* out;             /* fp16 (or fp32) [M, ldo] */
+  int32_t ldo;
+  int32_t out_fp32;
+  int32_t act;           /* UDT_ACT_* */
+  int32_t bn_hint;       /* column tile, 0 = library picks */
+} udt_igemm_desc;
+
 /* K2/K3 — segmented implicit GEMM on tcgen05/TMEM fed by TMA:
- *     out[m, n] = act( sum_seg sum_tap sum_c A_seg[pixel(m)+tap, c] * Wt[n, k(seg,tap,c)]
+ *     out[m, n] = act( sum_seg sum_tap sum_c A_seg[pixel(m)*stride+tap-pad, c] * Wt[n, k(seg,tap,c)]
  *                      + bias[n] + rowbias[image(m), n] ) + residual[m, n]
- * Replaces: nn.Conv2d 3x3 (openaimodel.py:186,223-229,85-87; model.py:108-117), 1x1 skip/nin_shortcut
- * (openaimodel.py:240; model.py:124-126) fused as an extra K segment, nn.Linear (attention.py:47,66,
- * 127-135,193-199,375,395; openaimodel.py:212-215,341-343), the `h + emb_out` add (openaimodel.py:266)
- * as `rowbias`, residual adds (openaimodel.py:268; attention.py:315-341,416) and GEGLU (attention.py:49-51).
- * `weight` is fp16 [N_out, K_total], K ordered (segment, tap = ky*3+kx, channel).  For UDT_ACT_GEGLU the
- * logical output has N_out/2 columns (see udt_geglu_tile()).  `residual` may alias `out`.
- * `rowbias` is fp32 [NB, ld_rowbias] (one row per image).  `bn_hint` = 0 lets the library pick the column tile. */
-int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int32_t H, int32_t W, const void* weight,
-              int32_t N_out, const float* bias, const float* rowbias, int32_t ld_rowbias, const void* residual,
-              int32_t ldr, void* out, int32_t ldo, int32_t out_fp32, int32_t act, int32_t bn_hint, void* stream);
+ * Replaces: nn.Conv2d 3x3 stride 1/2 (openaimodel.py:186,223-229,85-87,132-139; model.py:108-117,77-85), 1x1
+ * skip/nin_shortcut (openaimodel.py:240; model.py:124-126) fused as an extra K segment, nn.Linear
+ * (attention.py:47,66,127-135,193-199,375,395; openaimodel.py:212-215,341-343), the `h + emb_out` add
+ * (openaimodel.py:266) as `rowbias`, residual adds (openaimodel.py:268; attention.py:315-341,416) and GEGLU
+ * (attention.py:49-51).  For UDT_ACT_GEGLU the logical output has N_out/2 columns (see udt_geglu_tile()). */
+int udt_igemm(const udt_igemm_desc* desc, void* stream);
 /* column tile (BN) the GEGLU weight interleave must be packed for (x half then gate half per tile) */
 int udt_geglu_tile(void);
 
@@ -88,18 +109,44 @@ int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o, int32_t B
 int udt_xattn_small_l(const void* q, const void* kc, const void* vc, void* o, float* probs, int32_t B, int32_t N,
                       int32_t L, int32_t heads, int32_t ldq, int32_t ldkv, int32_t ldo, float scale, void* stream);
 
+/* LabelEncoder (encoders/modules.py:1088-1173): character embedding + sinusoid positional encoding,
+ * out fp16 [rows = B*L, D] = emb[idx[row], :] + pe[row % L, :] (emb fp32 [95, D], pe fp32 [L, D], idx int32), and
+ * the multi-head self-attention of its nn.TransformerEncoder layers over the fused in_proj output
+ * qkv fp16 [B*L, ld >= 3*heads*dh] (q | k | v), L <= 16 tokens, head dim <= 256, no mask:
+ * o fp16 [B*L, ldo] = softmax(q k^T * scale) v per head.  The projections / FFN run through udt_igemm. */
+int udt_label_embed(const int32_t* idx, const float* emb, const float* pe, void* out, int32_t rows, int32_t L,
+                    int32_t D, void* stream);
+int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int32_t heads, int32_t dh, int32_t ld, int32_t ldo,
+                  float scale, void* stream);
+
 /* row-wise softmax over fp16 [rows, cols] in place with a pre-scale (VAE single-head attention,
  * model.py:246-248, executed as GEMM -> softmax -> GEMM). */
 int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream);
 
 /* K7 — sampler glue (guiders.py:25-40, denoiser.py:22-28, wrappers.py:27, sampling_utils.py:39-40,
- * sampling.py:85-86,349-351), all on NHWC: x fp32 [B,HW,4].
- *  pack:  unet_in[2B,HW,16] fp16 <- cat(x * c_in, concat_{uc|c}) zero padded to 16 channels
- *  step:  eps = eps_u + scale*(eps_c - eps_u); x += (sigma_next - sigma) * eps            */
+ * sampling.py:85-86,349-351).  The sampler state keeps the reference's layout: x fp32 NCHW [B,4,HW], concat
+ * fp32 NCHW [B,5,HW]; the UNet side is NHWC.  The per-step scalars live in device memory (`c_in_dev`,
+ * `dsigma_dev` point at one fp32 each) so that one captured CUDA graph serves every step.
+ *  pack:  unet_in[2B,HW,16] fp16 <- cat(x * c_in, concat_{uc|c}) zero padded to 16 channels (uc half first)
+ *  step:  eps = eps_u + scale*(eps_c - eps_u); x += (sigma_next - sigma) * eps;  eps2b fp32 NHWC [2B,HW,4]   */
 int udt_cfg_pack(const float* x, const float* concat_uc, const float* concat_c, void* unet_in, int32_t B, int32_t HW,
-                 float c_in, void* stream);
-int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32_t HW, float cfg_scale, float dsigma,
+                 const float* c_in_dev, void* stream);
+int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32_t HW, float cfg_scale, const float* dsigma_dev,
                        void* stream);
+
+/* K10 — conditioner tail (encoders/modules.py:843-857,1011-1014,195-198; distributions.py:24-41):
+ * concat_{c,uc} fp32 NCHW [B,5,h*w] = cat(bilinear_1/8(mask), scale_factor * (mean + exp(0.5*clamp(logvar,-30,20)) * noise_{c,uc}))
+ * moments fp32 NHWC [B,h*w,ld_moments] (mean = channels 0..3, logvar = 4..7); noise fp32 NCHW [B,4,h*w];
+ * mask fp32 [B,1,8h,8w]. */
+int udt_vae_sample_pack(const float* moments, int32_t ld_moments, const float* noise_c, const float* noise_uc,
+                        const float* mask, float* concat_c, float* concat_uc, int32_t B, int32_t h, int32_t w,
+                        float scale_factor, void* stream);
+
+/* per-pixel affine map on <= 8 channels: out fp16 NHWC [B,HW,Cpad] = Wm[Cout,Cin] * (x[B,Cin,HW] * in_scale) + bias,
+ * channels >= Cout zero.  post_quant_conv with the 1/scale_factor of decode_first_stage folded in
+ * (autoencoder.py:313-316; diffusion.py:124-129). */
+int udt_pointwise_affine(const float* x, const float* Wm, const float* bias, void* out, int32_t B, int32_t HW,
+                         int32_t Cin, int32_t Cout, int32_t Cpad, float in_scale, void* stream);
 
 /* data movement helpers */
 /* nearest-neighbour 2x upsample of NHWC fp16 (openaimodel.py:99; model.py:65) */

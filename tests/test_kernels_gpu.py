@@ -148,6 +148,44 @@ def test_im2col_conv_paths(udt_lib, stride, pad_lo, cin):
     assert _rel(y.float().cpu().reshape(nb, ho, wo, cout).permute(0, 3, 1, 2), ref) < 2e-3
 
 
+@pytest.mark.parametrize("stride,pad,cin,cstore,h,w", [(1, 1, 9, 16, 32, 32), (2, 1, 64, 64, 32, 32), (2, 0, 32, 32, 32, 32),
+                                                      (2, 1, 320, 320, 64, 64), (2, 0, 128, 128, 64, 48), (1, 1, 3, 8, 40, 24),
+                                                      (2, 1, 640, 640, 16, 16), (2, 0, 512, 512, 8, 8)])
+def test_conv3x3_tma_stride_pad_and_narrow_channels(udt_lib, stride, pad, cin, cstore, h, w):
+    """first convs (Cin = 9 / 3 / 4 stored as 16 / 8 channels, zero-filled to 64 by TMA), UNet stride-2 (pad 1,
+    openaimodel.py:132-139) and the VAE stride-2 with pad (0,1,0,1) (model.py:77-85) through strided TMA boxes."""
+    from udifftext_b200 import ops, pack
+    dev = _dev()
+    g = torch.Generator().manual_seed(stride * 10 + cin + h)
+    nb, cout = 3, 128
+    x = _randn((nb, cin, h, w), g).half()
+    wt = _randn((cout, cin, 3, 3), g, 1 / math.sqrt(9 * cin)).half()
+    b = _randn((cout,), g)
+    if pad == 0:
+        ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wt.float(), b, stride=2)
+    else:
+        ref = F.conv2d(x.float(), wt.float(), b, stride=stride, padding=1)
+    xh = torch.zeros((nb, h, w, cstore), dtype=torch.float16)
+    xh[..., :cin] = x.permute(0, 2, 3, 1)
+    y = ops.conv3x3(xh.to(dev), pack.pack_conv3x3(wt.float(), cin_pad=cstore).to(dev), b.to(dev), stride=stride, pad=pad)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (nb, ref.shape[2], ref.shape[3], cout)
+    assert _rel(y.float().cpu().permute(0, 3, 1, 2), ref) < 2e-3
+
+
+def test_linear_strided_operands(udt_lib):
+    """x and weight as column slices of wider buffers (fused q|k buffer of the VAE attention): ld / ldw > K"""
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(77)
+    n, c = 320, 128
+    qk = _randn((n, 2 * c), g).half().to(dev)
+    s = ops.linear(qk[:, :c], qk[:, c:])
+    ref = qk[:, :c].float() @ qk[:, c:].float().t()
+    torch.cuda.synchronize()
+    assert _rel(s, ref) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------- norms
 @pytest.mark.parametrize("nb,hw,c0,c1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (3, 1024, 640, 320, True, 1e-5),
                                                   (2, 64, 1280, 1280, True, 1e-5), (2, 256, 1280, 0, False, 1e-6),
@@ -239,22 +277,23 @@ def test_sampler_glue_and_layout(udt_lib):
     dev = _dev()
     g = torch.Generator().manual_seed(9)
     b, hw = 3, 4096
-    x = _randn((b, hw, 4), g)
-    cu = _randn((b, hw, 5), g)
-    cc = _randn((b, hw, 5), g)
+    x = _randn((b, 4, hw), g)           # sampler state: reference layout NCHW
+    cu = _randn((b, 5, hw), g)
+    cc = _randn((b, 5, hw), g)
+    consts = torch.tensor([0.37, -0.3], device=dev)  # per-step scalars live in device memory
     out = torch.empty((2 * b, hw, 16), device=dev, dtype=torch.float16)
-    ops.cfg_pack(x.to(dev), cu.to(dev), cc.to(dev), 0.37, out)
+    ops.cfg_pack(x.to(dev), cu.to(dev), cc.to(dev), consts[0:1], out)
     ref = torch.zeros((2 * b, hw, 16))
-    ref[:b, :, :4] = x * 0.37
-    ref[b:, :, :4] = x * 0.37
-    ref[:b, :, 4:9] = cu
-    ref[b:, :, 4:9] = cc
+    ref[:b, :, :4] = (x * torch.tensor(0.37)).permute(0, 2, 1)
+    ref[b:, :, :4] = (x * torch.tensor(0.37)).permute(0, 2, 1)
+    ref[:b, :, 4:9] = cu.permute(0, 2, 1)
+    ref[b:, :, 4:9] = cc.permute(0, 2, 1)
     torch.cuda.synchronize()
     assert (out.float().cpu() - ref.half().float()).abs().max().item() == 0.0
-    eps = _randn((2 * b, hw, 4), g)
+    eps = _randn((2 * b, hw, 4), g)     # UNet output: NHWC fp32
     xd = x.to(dev).clone()
-    ops.cfg_euler_step_(xd, eps.to(dev), 5.0, -0.3)
-    ref2 = x + (-0.3) * (eps[:b] + 5.0 * (eps[b:] - eps[:b]))
+    ops.cfg_euler_step_(xd, eps.to(dev), 5.0, consts[1:2])
+    ref2 = x + (-0.3) * (eps[:b] + 5.0 * (eps[b:] - eps[:b])).permute(0, 2, 1)
     torch.cuda.synchronize()
     assert (xd.cpu() - ref2).abs().max().item() < 1e-5
     # layout conversions + upsample
@@ -271,3 +310,33 @@ def test_sampler_glue_and_layout(udt_lib):
     refu = F.interpolate(t.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
     torch.cuda.synchronize()
     assert (up.float().cpu() - refu).abs().max().item() == 0.0
+
+
+def test_vae_sample_pack_and_pointwise_affine(udt_lib):
+    """K10 against the oracle's posterior_sample / F.interpolate / cat, and post_quant_conv as a per-pixel affine map."""
+    from oracle import restated as R
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(21)
+    b, h, w = 2, 16, 24
+    moments = _randn((b, 8, h, w), g) * 3.0
+    moments[:, 4:] *= 6.0  # exercise the logvar clamp [-30, 20]
+    n_c, n_uc = _randn((b, 4, h, w), g), _randn((b, 4, h, w), g)
+    mask = (torch.rand((b, 1, 8 * h, 8 * w), generator=g) > 0.5).float()
+    mom_nhwc = moments.permute(0, 2, 3, 1).contiguous()
+    cat_c, cat_uc = ops.vae_sample_pack(mom_nhwc.to(dev), n_c.to(dev), n_uc.to(dev), mask.to(dev), 0.18215)
+    m8 = F.interpolate(mask, scale_factor=0.125, mode="bilinear")
+    ref_c = torch.cat([m8, 0.18215 * R.posterior_sample(moments, n_c)], dim=1)
+    ref_uc = torch.cat([m8, 0.18215 * R.posterior_sample(moments, n_uc)], dim=1)
+    torch.cuda.synchronize()
+    for got, ref in ((cat_c, ref_c), (cat_uc, ref_uc)):
+        err = (got.cpu() - ref).abs() / (1.0 + ref.abs())
+        assert err.max().item() < 1e-5
+    z = _randn((b, 4, h, w), g)
+    wm = _randn((4, 4), g)
+    bias = _randn((4,), g)
+    out = ops.pointwise_affine(z.to(dev), wm.to(dev), bias.to(dev), 8, 1.0 / 0.18215)
+    ref = F.conv2d(z / 0.18215, wm[:, :, None, None], bias).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert (out[..., :4].float().cpu() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    assert out[..., 4:].abs().max().item() == 0.0

@@ -100,6 +100,71 @@ __global__ void __launch_bounds__(kXaThreads) xattn_small_l_kernel(const __half*
   }
 }
 
+// ---------------------------------------------------------------------------------------------- LabelEncoder pieces
+// Character embedding + sinusoid positional encoding (encoders/modules.py:1160-1166, 1083-1085):
+// out fp16 [B*L, D] = emb[idx[b,l], :] + pe[l, :]
+__global__ void label_embed_kernel(const int32_t* __restrict__ idx, const float* __restrict__ emb,
+                                   const float* __restrict__ pe, __half* __restrict__ out, int rows, int L, int D) {
+  const size_t total = static_cast<size_t>(rows) * D;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(i % D);
+    const int r = static_cast<int>(i / D);
+    out[i] = __float2half_rn(emb[static_cast<size_t>(idx[r]) * D + d] + pe[static_cast<size_t>(r % L) * D + d]);
+  }
+}
+
+// Multi-head self-attention over a short sequence (L <= 16 tokens, head dim <= 256, no mask): the
+// nn.TransformerEncoderLayer attention of the LabelEncoder (encoders/modules.py:1103-1104).  One CTA per
+// (head, batch item); q/k/v are column blocks of the fused in_proj output [B*L, 3*D].
+constexpr int kMhaMaxL = 16;
+constexpr int kMhaMaxD = 256;
+constexpr int kMhaThreads = 128;
+
+__global__ void __launch_bounds__(kMhaThreads) mha_small_kernel(const __half* __restrict__ qkv, __half* __restrict__ o,
+                                                                int L, int heads, int dh, int ld, int ldo, float scale) {
+  __shared__ __half sq[kMhaMaxL * kMhaMaxD];
+  __shared__ __half sk[kMhaMaxL * kMhaMaxD];
+  __shared__ __half sv[kMhaMaxL * kMhaMaxD];
+  __shared__ float sp[kMhaMaxL * kMhaMaxL];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int D = heads * dh;
+  for (int i = threadIdx.x; i < L * dh; i += blockDim.x) {
+    const int l = i / dh, d = i % dh;
+    const size_t off = (static_cast<size_t>(b) * L + l) * ld + h * dh + d;
+    sq[i] = qkv[off];
+    sk[i] = qkv[off + D];
+    sv[i] = qkv[off + 2 * D];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+    const int i = e / L, j = e % L;
+    float acc = 0.0f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(__half2float(sq[i * dh + d]), __half2float(sk[j * dh + d]), acc);
+    sp[e] = acc * scale;
+  }
+  __syncthreads();
+  if (threadIdx.x < L) {
+    float* row = sp + threadIdx.x * L;
+    float mx = -INFINITY;
+    for (int j = 0; j < L; ++j) mx = fmaxf(mx, row[j]);
+    float sum = 0.0f;
+    for (int j = 0; j < L; ++j) {
+      row[j] = __expf(row[j] - mx);
+      sum += row[j];
+    }
+    const float inv = 1.0f / sum;
+    for (int j = 0; j < L; ++j) row[j] *= inv;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * dh; e += blockDim.x) {
+    const int i = e / dh, d = e % dh;
+    float acc = 0.0f;
+    for (int j = 0; j < L; ++j) acc = fmaf(sp[i * L + j], __half2float(sv[j * dh + d]), acc);
+    o[(static_cast<size_t>(b) * L + i) * ldo + h * dh + d] = __float2half_rn(acc);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- row softmax
 // One CTA per row; cols up to 16384 (VAE attention N = 4096 / 9216), values cached in registers.
 constexpr int kSmThreads = 256;
@@ -170,23 +235,27 @@ __global__ void __launch_bounds__(kSmThreads) softmax_rows_kernel(__half* __rest
 }
 
 // ---------------------------------------------------------------------------------------------- K7
+// Sampler state stays in the reference's layout (x fp32 NCHW [B,4,HW], concat fp32 NCHW [B,5,HW]); the UNet side
+// is NHWC.  Per-step scalars (c_in, sigma_next - sigma) are read from device memory so that one captured CUDA
+// graph serves every step.
 // unet_in[2B, HW, 16] fp16: rows [0,B) = uc half, [B,2B) = cond half (guiders.py:36: uc first).
 __global__ void cfg_pack_kernel(const float* __restrict__ x, const float* __restrict__ cat_uc,
-                                const float* __restrict__ cat_c, __half* __restrict__ out, int B, int HW, float c_in) {
+                                const float* __restrict__ cat_c, __half* __restrict__ out, int B, int HW,
+                                const float* __restrict__ c_in_dev) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 2B*HW pixels
   const int total = 2 * B * HW;
   if (idx >= total) return;
+  const float c_in = __ldg(c_in_dev);
   const int half_sel = idx / (B * HW);
   const int pix = idx % (B * HW);
-  const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(pix) * 4);
-  const float* cc = (half_sel == 0 ? cat_uc : cat_c) + static_cast<size_t>(pix) * 5;
+  const int b = pix / HW, p = pix % HW;
+  const float* xb = x + static_cast<size_t>(b) * 4 * HW + p;
+  const float* cc = (half_sel == 0 ? cat_uc : cat_c) + static_cast<size_t>(b) * 5 * HW + p;
   float f[16];
-  f[0] = xv.x * c_in;
-  f[1] = xv.y * c_in;
-  f[2] = xv.z * c_in;
-  f[3] = xv.w * c_in;
 #pragma unroll
-  for (int j = 0; j < 5; ++j) f[4 + j] = cc[j];
+  for (int j = 0; j < 4; ++j) f[j] = __ldg(xb + static_cast<size_t>(j) * HW) * c_in;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) f[4 + j] = __ldg(cc + static_cast<size_t>(j) * HW);
 #pragma unroll
   for (int j = 9; j < 16; ++j) f[j] = 0.0f;
   uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * 16);
@@ -201,20 +270,78 @@ __global__ void cfg_pack_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
-// x[B,HW,4] += dsigma * (eps_u + s*(eps_c - eps_u)); eps2b fp32 [2B,HW,4]
+// x[B,4,HW] (NCHW) += dsigma * (eps_u + s*(eps_c - eps_u)); eps2b fp32 NHWC [2B,HW,4]
 __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps, int B, int HW, float s,
-                                 float dsigma) {
+                                 const float* __restrict__ dsigma_dev) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = B * HW;
   if (idx >= total) return;
-  float4 xv = *reinterpret_cast<float4*>(x + static_cast<size_t>(idx) * 4);
+  const float dsigma = __ldg(dsigma_dev);
+  const int b = idx / HW, p = idx % HW;
   const float4 eu = *reinterpret_cast<const float4*>(eps + static_cast<size_t>(idx) * 4);
   const float4 ec = *reinterpret_cast<const float4*>(eps + (static_cast<size_t>(total) + idx) * 4);
-  xv.x += dsigma * (eu.x + s * (ec.x - eu.x));
-  xv.y += dsigma * (eu.y + s * (ec.y - eu.y));
-  xv.z += dsigma * (eu.z + s * (ec.z - eu.z));
-  xv.w += dsigma * (eu.w + s * (ec.w - eu.w));
-  *reinterpret_cast<float4*>(x + static_cast<size_t>(idx) * 4) = xv;
+  float* xb = x + static_cast<size_t>(b) * 4 * HW + p;
+  xb[0] += dsigma * (eu.x + s * (ec.x - eu.x));
+  xb[static_cast<size_t>(HW)] += dsigma * (eu.y + s * (ec.y - eu.y));
+  xb[static_cast<size_t>(2) * HW] += dsigma * (eu.z + s * (ec.z - eu.z));
+  xb[static_cast<size_t>(3) * HW] += dsigma * (eu.w + s * (ec.w - eu.w));
+}
+
+// ---------------------------------------------------------------------------------------------- K10
+// Conditioner tail: posterior sample of the masked-image latent for the c and the uc branch (two different
+// noise draws over the same moments), latent scale, 1/8 bilinear mask, channel concat.
+//   moments fp32 NHWC [B, HW, ldm] (mean 0..3, logvar 4..7); noise fp32 NCHW [B,4,HW]; mask fp32 [B,1,8h,8w]
+//   concat_{c,uc} fp32 NCHW [B,5,HW] = cat(mask8, scale * (mean + exp(0.5*clamp(logvar,-30,20)) * noise))
+__global__ void vae_sample_pack_kernel(const float* __restrict__ moments, int ldm, const float* __restrict__ noise_c,
+                                       const float* __restrict__ noise_uc, const float* __restrict__ mask,
+                                       float* __restrict__ cat_c, float* __restrict__ cat_uc, int B, int h, int w,
+                                       float scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = h * w;
+  if (idx >= B * HW) return;
+  const int b = idx / HW, p = idx % HW;
+  const int y = p / w, x = p % w;
+  // F.interpolate(scale_factor=0.125, bilinear, align_corners=False): source coordinate 8*i + 3.5
+  const int W8 = 8 * w;
+  const float* mb = mask + static_cast<size_t>(b) * (8 * h) * W8 + static_cast<size_t>(8 * y + 3) * W8 + (8 * x + 3);
+  const float m8 = 0.25f * (mb[0] + mb[1] + mb[W8] + mb[W8 + 1]);
+  const float* mo = moments + static_cast<size_t>(idx) * ldm;
+  const size_t o5 = static_cast<size_t>(b) * 5 * HW + p;
+  const size_t o4 = static_cast<size_t>(b) * 4 * HW + p;
+  cat_c[o5] = m8;
+  cat_uc[o5] = m8;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float mean = mo[c];
+    const float lv = fminf(fmaxf(mo[4 + c], -30.0f), 20.0f);
+    const float sd = expf(0.5f * lv);
+    cat_c[o5 + static_cast<size_t>(c + 1) * HW] = scale * (mean + sd * noise_c[o4 + static_cast<size_t>(c) * HW]);
+    cat_uc[o5 + static_cast<size_t>(c + 1) * HW] = scale * (mean + sd * noise_uc[o4 + static_cast<size_t>(c) * HW]);
+  }
+}
+
+// per-pixel small affine map (post_quant_conv, autoencoder.py:313-316 with the 1/scale_factor of
+// diffusion.py:125 folded into `in_scale`): out fp16 NHWC [B,HW,Cpad] = Wm[Cout,Cin] * (x[B,Cin,HW] * in_scale) + bias
+__global__ void pointwise_affine_kernel(const float* __restrict__ x, const float* __restrict__ Wm,
+                                        const float* __restrict__ bias, __half* __restrict__ out, int B, int HW, int Cin,
+                                        int Cout, int Cpad, float in_scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * HW) return;
+  const int b = idx / HW, p = idx % HW;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = (k < Cin) ? x[(static_cast<size_t>(b) * Cin + k) * HW + p] * in_scale : 0.0f;
+  __half* o = out + static_cast<size_t>(idx) * Cpad;
+  for (int c = 0; c < Cpad; ++c) {
+    float acc = 0.0f;
+    if (c < Cout) {
+      acc = bias != nullptr ? __ldg(bias + c) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < Cin) acc = fmaf(__ldg(Wm + c * Cin + k), v[k], acc);
+    }
+    o[c] = __float2half_rn(acc);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- movement
@@ -310,6 +437,29 @@ extern "C" int udt_xattn_small_l(const void* q, const void* kc, const void* vc, 
   return check_launch("udt_xattn_small_l");
 }
 
+extern "C" int udt_label_embed(const int32_t* idx, const float* emb, const float* pe, void* out, int32_t rows,
+                               int32_t L, int32_t D, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (rows < 1 || L < 1 || D < 1) return fail(UDT_ERR_SHAPE, "udt_label_embed: rows=%d L=%d D=%d", rows, L, D);
+  const size_t total = static_cast<size_t>(rows) * D;
+  label_embed_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      idx, emb, pe, reinterpret_cast<__half*>(out), rows, L, D);
+  return check_launch("udt_label_embed");
+}
+
+extern "C" int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int32_t heads, int32_t dh, int32_t ld,
+                             int32_t ldo, float scale, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (L < 1 || L > kMhaMaxL || dh < 1 || dh > kMhaMaxD || B < 1 || heads < 1 || ld < 3 * heads * dh)
+    return fail(UDT_ERR_SHAPE, "udt_mha_small: L=%d (<=%d) dh=%d (<=%d) ld=%d", L, kMhaMaxL, dh, kMhaMaxD, ld);
+  dim3 grid(heads, B);
+  mha_small_kernel<<<grid, kMhaThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(o), L, heads, dh, ld, ldo, scale);
+  return check_launch("udt_mha_small");
+}
+
 extern "C" int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream) {
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
@@ -321,23 +471,49 @@ extern "C" int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld,
 }
 
 extern "C" int udt_cfg_pack(const float* x, const float* concat_uc, const float* concat_c, void* unet_in, int32_t B,
-                            int32_t HW, float c_in, void* stream) {
+                            int32_t HW, const float* c_in_dev, void* stream) {
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
+  if (B < 1 || HW < 1 || c_in_dev == nullptr) return fail(UDT_ERR_SHAPE, "udt_cfg_pack: B=%d HW=%d", B, HW);
   const int total = 2 * B * HW;
   cfg_pack_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, concat_uc, concat_c, reinterpret_cast<__half*>(unet_in), B, HW, c_in);
+      x, concat_uc, concat_c, reinterpret_cast<__half*>(unet_in), B, HW, c_in_dev);
   return check_launch("udt_cfg_pack");
 }
 
-extern "C" int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32_t HW, float cfg_scale, float dsigma,
-                                  void* stream) {
+extern "C" int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32_t HW, float cfg_scale,
+                                  const float* dsigma_dev, void* stream) {
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
+  if (B < 1 || HW < 1 || dsigma_dev == nullptr) return fail(UDT_ERR_SHAPE, "udt_cfg_euler_step: B=%d HW=%d", B, HW);
   const int total = B * HW;
   cfg_euler_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, eps2b, B, HW, cfg_scale,
-                                                                                          dsigma);
+                                                                                          dsigma_dev);
   return check_launch("udt_cfg_euler_step");
+}
+
+extern "C" int udt_vae_sample_pack(const float* moments, int32_t ld_moments, const float* noise_c, const float* noise_uc,
+                                   const float* mask, float* concat_c, float* concat_uc, int32_t B, int32_t h, int32_t w,
+                                   float scale_factor, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (B < 1 || h < 1 || w < 1 || ld_moments < 8) return fail(UDT_ERR_SHAPE, "udt_vae_sample_pack: B=%d h=%d w=%d ld=%d", B, h, w, ld_moments);
+  const int total = B * h * w;
+  vae_sample_pack_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      moments, ld_moments, noise_c, noise_uc, mask, concat_c, concat_uc, B, h, w, scale_factor);
+  return check_launch("udt_vae_sample_pack");
+}
+
+extern "C" int udt_pointwise_affine(const float* x, const float* Wm, const float* bias, void* out, int32_t B, int32_t HW,
+                                    int32_t Cin, int32_t Cout, int32_t Cpad, float in_scale, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (B < 1 || HW < 1 || Cin < 1 || Cin > 8 || Cout < 1 || Cout > Cpad)
+    return fail(UDT_ERR_SHAPE, "udt_pointwise_affine: Cin=%d (1..8) Cout=%d Cpad=%d", Cin, Cout, Cpad);
+  const int total = B * HW;
+  pointwise_affine_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, Wm, bias, reinterpret_cast<__half*>(out), B, HW, Cin, Cout, Cpad, in_scale);
+  return check_launch("udt_pointwise_affine");
 }
 
 extern "C" int udt_upsample2x_nhwc(const void* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream) {

@@ -87,11 +87,13 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* m, const void* ptr, uint32_t rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, const cuuint32_t* estr_in = nullptr) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return fail(UDT_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(UDT_ERR_ALIGN, "TMA base pointer not 16-byte aligned");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (estr_in != nullptr)
+    for (uint32_t i = 0; i < rank; ++i) estr[i] = estr_in[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -111,12 +113,14 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, 
 }
 
 int make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld,
-                   uint32_t bw, uint32_t bh, uint32_t bn) {
+                   uint32_t bw, uint32_t bh, uint32_t bn, uint32_t pix_stride) {
   if ((ld * 2) % 16 != 0) return fail(UDT_ERR_ALIGN, "channel pitch %llu elements is not a multiple of 8", (unsigned long long)ld);
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {ld * 2, ld * 2 * W, ld * 2 * W * H};
-  cuuint32_t box[4] = {64, bw, bh, bn};
-  return encode(m, ptr, 4, dims, strides, box);
+  // a box of bw x bh *loaded* pixels spans bw*stride x bh*stride tensor elements (TMA traversal stride)
+  cuuint32_t box[4] = {64, bw * pix_stride, bh * pix_stride, bn};
+  cuuint32_t estr[4] = {1, pix_stride, pix_stride, 1};
+  return encode(m, ptr, 4, dims, strides, box, estr);
 }
 
 }  // namespace udt_host

@@ -21,8 +21,9 @@ int arch();                           // compute capability * 10 of the current 
 // 2-D fp16 tensor map, dim0 = contiguous (cols), box = {box0, box1}, 128B swizzle.
 int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box0,
                  uint32_t box1);
-// 4-D fp16 NHWC tensor map: dims (C, W, H, N), channel pitch `ld` elements, box = {64, bw, bh, bn}, 128B swizzle.
+// 4-D fp16 NHWC tensor map: dims (C, W, H, N), channel pitch `ld` elements, box = {64, bw, bh, bn} loaded pixels
+// taken every `pix_stride`-th pixel along W and H (TMA element strides), 128B swizzle.
 int make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld,
-                   uint32_t bw, uint32_t bh, uint32_t bn);
+                   uint32_t bw, uint32_t bh, uint32_t bn, uint32_t pix_stride);
 
 }  // namespace udt_host

@@ -36,6 +36,8 @@ struct IGemmParams {
   CUtensorMap mapB;
   int32_t seg_kc[3];
   int32_t seg_taps[3];
+  int32_t seg_stride[3];
+  int32_t seg_pad[3];
   int32_t nseg, ksteps;
   int32_t W, H, NB;
   int32_t bw, bh, bn;
@@ -84,6 +86,9 @@ __device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[
   if (p.act == UDT_ACT_SILU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+  } else if (p.act == UDT_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
   }
   if (p.out_fp32) {
     float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col;
@@ -181,13 +186,14 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           const CUtensorMap* ma = &p.mapA[s];
           const int taps = p.seg_taps[s];
           const int kc = p.seg_kc[s];
+          const int sw0 = tc.w0 * p.seg_stride[s], sh0 = tc.h0 * p.seg_stride[s];
           for (int t = 0; t < taps; ++t) {
-            const int dy = (taps == 9) ? (t / 3 - 1) : 0;
-            const int dx = (taps == 9) ? (t % 3 - 1) : 0;
+            const int dy = (taps == 9) ? (t / 3 - p.seg_pad[s]) : 0;
+            const int dx = (taps == 9) ? (t % 3 - p.seg_pad[s]) : 0;
             for (int c = 0; c < kc; ++c, ++kstep) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(kABytes + b_bytes));
-              tma_load_4d(ma, &full_bar[stage], sA + stage * kABytes, c * kBlockK, tc.w0 + dx, tc.h0 + dy, tc.n0);
+              tma_load_4d(ma, &full_bar[stage], sA + stage * kABytes, c * kBlockK, sw0 + dx, sh0 + dy, tc.n0);
               tma_load_2d(&p.mapB, &full_bar[stage], sB + stage * b_bytes, kstep * kBlockK, tc.n_blk * p.BN);
               if (++stage == p.stages) {
                 stage = 0;
@@ -361,17 +367,17 @@ int pick_bn(int N_out, int tiles_m, int act, int sms) {
 
 extern "C" int udt_geglu_tile(void) { return kGegluTile; }
 
-extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int32_t H, int32_t W, const void* weight,
-                         int32_t N_out, const float* bias, const float* rowbias, int32_t ld_rowbias, const void* residual,
-                         int32_t ldr, void* out, int32_t ldo, int32_t out_fp32, int32_t act, int32_t bn_hint,
-                         void* stream) {
+extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   using namespace udt_host;
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
+  if (d == nullptr) return fail(UDT_ERR_SHAPE, "udt_igemm: null descriptor");
+  const int nsrc = d->nsrc, NB = d->NB, H = d->H, W = d->W, N_out = d->N_out, act = d->act;
   if (nsrc < 1 || nsrc > 3) return fail(UDT_ERR_SHAPE, "udt_igemm: nsrc=%d (1..3)", nsrc);
   if (NB < 1 || H < 1 || W < 1 || N_out < 1) return fail(UDT_ERR_SHAPE, "udt_igemm: bad shape NB=%d H=%d W=%d N=%d", NB, H, W, N_out);
-  if (act == UDT_ACT_GEGLU && (N_out % (2 * 32) != 0 || N_out % kGegluTile != 0 || out_fp32 || residual || rowbias))
+  if (act == UDT_ACT_GEGLU && (N_out % (2 * 32) != 0 || N_out % kGegluTile != 0 || d->out_fp32 || d->residual || d->rowbias))
     return fail(UDT_ERR_SHAPE, "udt_igemm: GEGLU needs N_out %% %d == 0, fp16 out, no residual/rowbias", kGegluTile);
+  if (d->out == nullptr || d->weight == nullptr) return fail(UDT_ERR_SHAPE, "udt_igemm: null out / weight");
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -380,15 +386,23 @@ extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int
     attr_set = true;
   }
 
+  int max_stride = 1;
+  for (int s = 0; s < nsrc; ++s) {
+    const int st = d->src[s].stride > 0 ? d->src[s].stride : 1;
+    if (st != 1 && st != 2) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d stride=%d (1 or 2)", s, st);
+    if (st > max_stride) max_stride = st;
+  }
+
   IGemmParams p;
   memset(&p, 0, sizeof(p));
-  // spatial tile: bw*bh*bn == 128, fewest tiles, prefer wide boxes
+  // spatial tile: bw*bh*bn == 128, fewest tiles, prefer wide boxes (TMA box extent bw*stride <= 256)
   {
     long best_tiles = -1;
     for (int bw = 128; bw >= 1; bw >>= 1) {
       for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
         const int bn = 128 / (bw * bh);
         if (bw > 2 * W && bw > 1) continue;
+        if (bw * max_stride > 256 || bh * max_stride > 256) continue;
         const long t = static_cast<long>((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((NB + bn - 1) / bn);
         if (best_tiles < 0 || t < best_tiles) {
           best_tiles = t;
@@ -407,7 +421,7 @@ extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int
   p.tiles_nb = (NB + p.bn - 1) / p.bn;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_nb;
   const int sms = num_sms();
-  int BN = bn_hint > 0 ? bn_hint : pick_bn(N_out, tiles_m, act, sms);
+  int BN = d->bn_hint > 0 ? d->bn_hint : pick_bn(N_out, tiles_m, act, sms);
   if (BN != 16 && (BN % 32 != 0 || BN < 32 || BN > 256)) return fail(UDT_ERR_SHAPE, "udt_igemm: BN=%d unsupported", BN);
   if (act == UDT_ACT_GEGLU && BN != kGegluTile) return fail(UDT_ERR_SHAPE, "udt_igemm: GEGLU requires BN=%d", kGegluTile);
   p.BN = BN;
@@ -418,19 +432,29 @@ extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int
   int ktotal = 0;
   p.nseg = nsrc;
   for (int s = 0; s < nsrc; ++s) {
-    const udt_gemm_src& a = srcs[s];
-    if (a.C < 64 || a.C % 64 != 0) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d has C=%d (multiple of 64 required)", s, a.C);
+    const udt_gemm_src& a = d->src[s];
+    const int st = a.stride > 0 ? a.stride : 1;
+    const int Hs = a.H > 0 ? a.H : H * st, Ws = a.W > 0 ? a.W : W * st;
+    if (a.C < 8 || a.C % 8 != 0) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d has C=%d (multiple of 8 required)", s, a.C);
     if (a.taps != 1 && a.taps != 9) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d taps=%d (1 or 9)", s, a.taps);
     if (a.ld < a.C) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d ld=%d < C=%d", s, a.ld, a.C);
-    rc = make_tmap_nhwc(&p.mapA[s], a.ptr, a.C, W, H, NB, a.ld, p.bw, p.bh, p.bn);
+    if (a.taps == 9 && a.pad != 0 && a.pad != 1) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d pad=%d (0 or 1)", s, a.pad);
+    if (a.taps == 1 && st != 1) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d: point-wise segments must have stride 1", s);
+    rc = make_tmap_nhwc(&p.mapA[s], a.ptr, a.C, Ws, Hs, NB, a.ld, p.bw, p.bh, p.bn, st);
     if (rc != UDT_OK) return rc;
-    p.seg_kc[s] = a.C / 64;
+    p.seg_kc[s] = (a.C + 63) / 64;  // channels are zero-filled by TMA up to the next multiple of 64
     p.seg_taps[s] = a.taps;
-    ktotal += a.taps * a.C;
+    p.seg_stride[s] = st;
+    p.seg_pad[s] = a.pad;
+    ktotal += a.taps * p.seg_kc[s] * 64;
   }
   p.ksteps = ktotal / 64;
-  rc = make_tmap_2d(&p.mapB, weight, static_cast<uint64_t>(ktotal), static_cast<uint64_t>(N_out),
-                    static_cast<uint64_t>(ktotal), 64, static_cast<uint32_t>(BN));
+  // a plain GEMM (one point-wise segment) may pass an unpadded [N_out, C] weight: TMA zero-fills the K tail
+  const int kdim_b = (nsrc == 1 && d->src[0].taps == 1) ? d->src[0].C : ktotal;
+  const int ldw = d->ldw > 0 ? d->ldw : kdim_b;
+  if (ldw < kdim_b) return fail(UDT_ERR_SHAPE, "udt_igemm: ldw=%d < K=%d (conv weights must be packed per 64-channel block)", ldw, kdim_b);
+  rc = make_tmap_2d(&p.mapB, d->weight, static_cast<uint64_t>(kdim_b), static_cast<uint64_t>(N_out),
+                    static_cast<uint64_t>(ldw), 64, static_cast<uint32_t>(BN));
   if (rc != UDT_OK) return rc;
 
   const int stage_bytes = kABytes + BN * kBlockK * 2;
@@ -438,14 +462,14 @@ extern "C" int udt_igemm(const udt_gemm_src* srcs, int32_t nsrc, int32_t NB, int
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(UDT_ERR_SHAPE, "udt_igemm: tile does not fit shared memory");
   p.stages = stages;
-  p.bias = bias;
-  p.rowbias = rowbias;
-  p.ld_rowbias = ld_rowbias;
-  p.residual = reinterpret_cast<const __half*>(residual);
-  p.ldr = ldr;
-  p.out = out;
-  p.ldo = ldo;
-  p.out_fp32 = out_fp32;
+  p.bias = d->bias;
+  p.rowbias = d->rowbias;
+  p.ld_rowbias = d->ld_rowbias;
+  p.residual = reinterpret_cast<const __half*>(d->residual);
+  p.ldr = d->ldr;
+  p.out = d->out;
+  p.ldo = d->ldo;
+  p.out_fp32 = d->out_fp32;
   p.act = act;
 
   const int smem = kCtrlBytes + 1024 + stages * stage_bytes;

@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_vo
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libudt_b200.so")
 
-UDT_ACT_NONE, UDT_ACT_SILU, UDT_ACT_GEGLU = 0, 1, 2
+UDT_ACT_NONE, UDT_ACT_SILU, UDT_ACT_GEGLU, UDT_ACT_RELU = 0, 1, 2, 3
 
 
 class UdtError(RuntimeError):
@@ -22,7 +22,17 @@ class UdtError(RuntimeError):
 class GemmSrc(Structure):
     """mirror of `udt_gemm_src`"""
 
-    _fields_ = [("ptr", c_void_p), ("C", c_int32), ("ld", c_int32), ("taps", c_int32)]
+    _fields_ = [("ptr", c_void_p), ("C", c_int32), ("ld", c_int32), ("taps", c_int32), ("H", c_int32), ("W", c_int32),
+                ("stride", c_int32), ("pad", c_int32)]
+
+
+class IGemmDesc(Structure):
+    """mirror of `udt_igemm_desc`"""
+
+    _fields_ = [("src", GemmSrc * 3), ("nsrc", c_int32), ("NB", c_int32), ("H", c_int32), ("W", c_int32),
+                ("weight", c_void_p), ("ldw", c_int32), ("N_out", c_int32), ("bias", c_void_p), ("rowbias", c_void_p),
+                ("ld_rowbias", c_int32), ("residual", c_void_p), ("ldr", c_int32), ("out", c_void_p), ("ldo", c_int32),
+                ("out_fp32", c_int32), ("act", c_int32), ("bn_hint", c_int32)]
 
 
 # name -> (restype, argtypes): every symbol include/udt_api.h declares
@@ -32,8 +42,7 @@ _PROTOTYPES = {
     "udt_last_error": (c_char_p, []),
     "udt_num_sms": (c_int32, []),
     "udt_geglu_tile": (c_int32, []),
-    "udt_igemm": (c_int32, [POINTER(GemmSrc), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
-                            c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "udt_igemm": (c_int32, [POINTER(IGemmDesc), c_void_p]),
     "udt_groupnorm_ws_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "udt_groupnorm_nhwc": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                      c_void_p, c_float, c_int32, c_void_p, c_void_p]),
@@ -42,9 +51,15 @@ _PROTOTYPES = {
                                c_int32, c_int32, c_float, c_void_p]),
     "udt_xattn_small_l": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "udt_label_embed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "udt_mha_small": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "udt_softmax_rows": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
-    "udt_cfg_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
-    "udt_cfg_euler_step": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p]),
+    "udt_cfg_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "udt_cfg_euler_step": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p]),
+    "udt_vae_sample_pack": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                      c_int32, c_float, c_void_p]),
+    "udt_pointwise_affine": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       c_float, c_void_p]),
     "udt_upsample2x_nhwc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "udt_im2col3x3_nhwc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_int32, c_int32, c_void_p]),

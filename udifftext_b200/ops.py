@@ -11,7 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import lib as _lib
-from .lib import UDT_ACT_GEGLU, UDT_ACT_NONE, UDT_ACT_SILU, GemmSrc  # noqa: F401
+from .lib import UDT_ACT_GEGLU, UDT_ACT_NONE, UDT_ACT_RELU, UDT_ACT_SILU, GemmSrc, IGemmDesc  # noqa: F401
 
 
 def _stream() -> int:
@@ -29,7 +29,7 @@ def _need(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
 
 
 def igemm(
-    srcs: Sequence[Tuple[torch.Tensor, int, int, int]],
+    srcs: Sequence[tuple],
     nb: int, h: int, w: int,
     weight: torch.Tensor,
     n_out: int,
@@ -39,30 +39,38 @@ def igemm(
     rowbias: Optional[torch.Tensor] = None,
     residual: Optional[torch.Tensor] = None,
     ldr: int = 0,
-    ld_rowbias: int = 0,
+    ld_rowbias: Optional[int] = None,
     out_fp32: bool = False,
     act: int = UDT_ACT_NONE,
     bn_hint: int = 0,
 ) -> torch.Tensor:
-    """Segmented implicit GEMM (udt_igemm).  `srcs` = [(tensor, C, ld, taps), ...]."""
+    """Segmented implicit GEMM (udt_igemm).  `srcs` = [(tensor, C, ld, taps[, stride, pad, H_in, W_in]), ...];
+    (nb, h, w) are the OUTPUT pixel dims; 3x3 segments default to stride 1 / pad 1."""
     L = _lib.load()
-    arr = (GemmSrc * len(srcs))()
-    for i, (t, c, ld, taps) in enumerate(srcs):
-        arr[i].ptr = t.data_ptr()
-        arr[i].C = c
-        arr[i].ld = ld
-        arr[i].taps = taps
-    rc = L.udt_igemm(arr, len(srcs), nb, h, w, weight.data_ptr(), n_out, _ptr(bias), _ptr(rowbias),
-                     (ld_rowbias or n_out) if rowbias is not None else 0, _ptr(residual), ldr,
-                     out.data_ptr(), ldo, int(out_fp32), act, bn_hint, _stream())
-    _lib.check(rc, "udt_igemm")
+    d = IGemmDesc()
+    for i, src in enumerate(srcs):
+        t, c, ld, taps = src[:4]
+        g = d.src[i]
+        g.ptr, g.C, g.ld, g.taps = t.data_ptr(), c, ld, taps
+        g.stride = src[4] if len(src) > 4 else 1
+        g.pad = src[5] if len(src) > 5 else (1 if taps == 9 else 0)
+        g.H = src[6] if len(src) > 6 else 0
+        g.W = src[7] if len(src) > 7 else 0
+    d.nsrc, d.NB, d.H, d.W = len(srcs), nb, h, w
+    d.weight, d.ldw, d.N_out = weight.data_ptr(), weight.stride(0), n_out
+    d.bias, d.rowbias = _ptr(bias), _ptr(rowbias)
+    d.ld_rowbias = 0 if rowbias is None else (n_out if ld_rowbias is None else ld_rowbias)
+    d.residual, d.ldr = _ptr(residual), ldr
+    d.out, d.ldo, d.out_fp32, d.act, d.bn_hint = out.data_ptr(), ldo, int(out_fp32), act, bn_hint
+    _lib.check(L.udt_igemm(ctypes.byref(d), _stream()), "udt_igemm")
     return out
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, act: int = UDT_ACT_NONE,
            out_fp32: bool = False, bn_hint: int = 0) -> torch.Tensor:
-    """y[M, N] = act(x[M, K] @ weight[N, K]^T + bias) (+ residual); fp16 in, fp16 (or fp32) out."""
+    """y[M, N] = act(x[M, K] @ weight[N, K]^T + bias) (+ residual); fp16 in, fp16 (or fp32) out.  `x` and `weight`
+    may be row-strided 2-D views (unit column stride)."""
     m, k = x.shape
     n = weight.shape[0]
     n_log = n // 2 if act == UDT_ACT_GEGLU else n
@@ -75,17 +83,21 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
             rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
             skip_srcs: Sequence[torch.Tensor] = (), out: Optional[torch.Tensor] = None, out_fp32: bool = False,
-            bn_hint: int = 0) -> torch.Tensor:
-    """3x3 / stride 1 / pad 1 conv on NHWC fp16 with packed weight [Cout, 9*Cin (+ sum skip C)];
-    `skip_srcs` are extra NHWC tensors consumed point-wise (fused 1x1 skip connection)."""
+            bn_hint: int = 0, stride: int = 1, pad: int = 1, ld_rowbias: Optional[int] = None) -> torch.Tensor:
+    """3x3 conv on NHWC fp16 (stride 1 or 2; pad = low-side zero padding, the high side is padded as needed) with
+    packed weight [Cout, 9*round_up(Cin,64) (+ skip segments)]; `skip_srcs` are extra NHWC tensors of the OUTPUT
+    size consumed point-wise (fused 1x1 skip connection)."""
     nb, h, w, c = x.shape
+    ho, wo = ((h + 2 * pad - 3) // stride + 1, (w + 2 * pad - 3) // stride + 1) if pad else (h // stride, w // stride)
     n = weight.shape[0]
     if out is None:
-        out = torch.empty((nb, h, w, n), device=x.device, dtype=torch.float32 if out_fp32 else torch.float16)
-    srcs = [(x, c, c, 9)] + [(s, s.shape[-1], s.shape[-1], 1) for s in skip_srcs]
-    return igemm(srcs, nb, h, w, weight, n, out, n, bias=bias, rowbias=rowbias, residual=residual,
-                 ldr=0 if residual is None else residual.shape[-1], out_fp32=out_fp32, bn_hint=bn_hint,
-                 ld_rowbias=0 if rowbias is None else rowbias.stride(0))
+        out = torch.empty((nb, ho, wo, n), device=x.device, dtype=torch.float32 if out_fp32 else torch.float16)
+    srcs = [(x, c, x.stride(2), 9, stride, pad, h, w)] + [(s, s.shape[-1], s.stride(2), 1) for s in skip_srcs]
+    if rowbias is not None and ld_rowbias is None:
+        ld_rowbias = rowbias.stride(0) if rowbias.dim() == 2 else 0
+    return igemm(srcs, nb, ho, wo, weight, n, out, out.stride(2), bias=bias, rowbias=rowbias, residual=residual,
+                 ldr=0 if residual is None else residual.stride(2), out_fp32=out_fp32, bn_hint=bn_hint,
+                 ld_rowbias=ld_rowbias)
 
 
 def groupnorm_ws_bytes(nb: int, hw: int, c: int, groups: int = 32) -> int:
@@ -147,6 +159,29 @@ def xattn_small_l(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, b: int, n
     return out
 
 
+def label_embed(idx: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
+    """idx int32 [B, L]; emb fp32 [V, D]; pe fp32 [L, D] -> fp16 [B*L, D]"""
+    L = _lib.load()
+    b, l = idx.shape
+    d = emb.shape[1]
+    out = torch.empty((b * l, d), device=emb.device, dtype=torch.float16)
+    _lib.check(L.udt_label_embed(idx.data_ptr(), emb.data_ptr(), pe.data_ptr(), out.data_ptr(), b * l, l, d, _stream()),
+               "udt_label_embed")
+    return out
+
+
+def mha_small(qkv: torch.Tensor, b: int, l: int, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv fp16 [B*L, 3*D] (q | k | v) -> fp16 [B*L, D]; softmax scale = head_dim^-0.5"""
+    L = _lib.load()
+    d = qkv.shape[1] // 3
+    dh = d // heads
+    if out is None:
+        out = torch.empty((b * l, d), device=qkv.device, dtype=torch.float16)
+    _lib.check(L.udt_mha_small(qkv.data_ptr(), out.data_ptr(), b, l, heads, dh, qkv.stride(0), out.stride(0),
+                               float(dh) ** -0.5, _stream()), "udt_mha_small")
+    return out
+
+
 def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
     L = _lib.load()
     rows, cols = x.shape
@@ -154,22 +189,49 @@ def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
     return x
 
 
-def cfg_pack(x: torch.Tensor, cat_uc: torch.Tensor, cat_c: torch.Tensor, c_in: float, out: torch.Tensor) -> torch.Tensor:
+def cfg_pack(x: torch.Tensor, cat_uc: torch.Tensor, cat_c: torch.Tensor, c_in_dev: torch.Tensor, out: torch.Tensor
+             ) -> torch.Tensor:
+    """x fp32 NCHW [B,4,h,w], cat_* fp32 NCHW [B,5,h,w], c_in_dev: device fp32 scalar -> out fp16 NHWC [2B,h,w,16]"""
     L = _lib.load()
     b = x.shape[0]
     hw = x.numel() // (b * 4)
-    _lib.check(L.udt_cfg_pack(x.data_ptr(), cat_uc.data_ptr(), cat_c.data_ptr(), out.data_ptr(), b, hw, float(c_in),
-                              _stream()), "udt_cfg_pack")
+    _lib.check(L.udt_cfg_pack(x.data_ptr(), cat_uc.data_ptr(), cat_c.data_ptr(), out.data_ptr(), b, hw,
+                              c_in_dev.data_ptr(), _stream()), "udt_cfg_pack")
     return out
 
 
-def cfg_euler_step_(x: torch.Tensor, eps2b: torch.Tensor, cfg_scale: float, dsigma: float) -> torch.Tensor:
+def cfg_euler_step_(x: torch.Tensor, eps2b: torch.Tensor, cfg_scale: float, dsigma_dev: torch.Tensor) -> torch.Tensor:
+    """x fp32 NCHW [B,4,h,w] += dsigma * cfg(eps2b fp32 NHWC [2B,h,w,4]); dsigma_dev: device fp32 scalar"""
     L = _lib.load()
     b = x.shape[0]
     hw = x.numel() // (b * 4)
-    _lib.check(L.udt_cfg_euler_step(x.data_ptr(), eps2b.data_ptr(), b, hw, float(cfg_scale), float(dsigma), _stream()),
-               "udt_cfg_euler_step")
+    _lib.check(L.udt_cfg_euler_step(x.data_ptr(), eps2b.data_ptr(), b, hw, float(cfg_scale), dsigma_dev.data_ptr(),
+                                    _stream()), "udt_cfg_euler_step")
     return x
+
+
+def vae_sample_pack(moments: torch.Tensor, noise_c: torch.Tensor, noise_uc: torch.Tensor, mask: torch.Tensor,
+                    scale_factor: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """moments fp32 NHWC [B,h,w,>=8]; noise fp32 NCHW [B,4,h,w]; mask fp32 [B,1,8h,8w] -> (concat_c, concat_uc) NCHW"""
+    L = _lib.load()
+    b, h, w, ld = moments.shape
+    cat_c = torch.empty((b, 5, h, w), device=moments.device, dtype=torch.float32)
+    cat_uc = torch.empty_like(cat_c)
+    _lib.check(L.udt_vae_sample_pack(moments.data_ptr(), ld, noise_c.data_ptr(), noise_uc.data_ptr(), mask.data_ptr(),
+                                     cat_c.data_ptr(), cat_uc.data_ptr(), b, h, w, float(scale_factor), _stream()),
+               "udt_vae_sample_pack")
+    return cat_c, cat_uc
+
+
+def pointwise_affine(x: torch.Tensor, wm: torch.Tensor, bias: Optional[torch.Tensor], cpad: int, in_scale: float
+                     ) -> torch.Tensor:
+    """x fp32 NCHW [B,Cin,h,w] -> fp16 NHWC [B,h,w,cpad] = wm @ (x * in_scale) + bias"""
+    L = _lib.load()
+    b, cin, h, w = x.shape
+    out = torch.empty((b, h, w, cpad), device=x.device, dtype=torch.float16)
+    _lib.check(L.udt_pointwise_affine(x.data_ptr(), wm.data_ptr(), _ptr(bias), out.data_ptr(), b, h * w, cin, wm.shape[0],
+                                      cpad, float(in_scale), _stream()), "udt_pointwise_affine")
+    return out
 
 
 def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

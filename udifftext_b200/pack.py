@@ -9,19 +9,38 @@ import torch
 GEGLU_TILE = 128  # must equal udt_geglu_tile()
 
 
-def pack_conv3x3(w_oihw: torch.Tensor, skip_1x1: Sequence[torch.Tensor] = ()) -> torch.Tensor:
-    """[O, I, 3, 3] -> fp16 [O, 9*I (+ sum of skip I)] with K ordered (tap = ky*3 + kx, channel); optional 1x1
-    skip-connection weights ([O, I_s, 1, 1] or [O, I_s]) are appended as extra K segments."""
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def _pad_k(w2d: torch.Tensor) -> torch.Tensor:
+    """[O, K] -> [O, round_up(K, 64)] zero padded (TMA zero-fills the activation side of the same K block)"""
+    o, k = w2d.shape
+    if k % 64 == 0:
+        return w2d
+    out = w2d.new_zeros((o, _pad64(k)))
+    out[:, :k] = w2d
+    return out
+
+
+def pack_conv3x3(w_oihw: torch.Tensor, skip_1x1: Sequence[torch.Tensor] = (), cin_pad: Optional[int] = None) -> torch.Tensor:
+    """[O, I, 3, 3] -> fp16 [O, 9*I64 (+ sum of skip I64)] with K ordered (tap = ky*3 + kx, channel) and every
+    tap's channel block zero padded to a multiple of 64 (I64); optional 1x1 skip-connection weights
+    ([O, I_s, 1, 1] or [O, I_s]) are appended as extra K segments.  `cin_pad` (>= I) is the channel count of the
+    activation tensor when it is stored wider than I (zero channels)."""
     o, i, kh, kw = w_oihw.shape
     assert (kh, kw) == (3, 3)
-    parts = [w_oihw.permute(0, 2, 3, 1).reshape(o, 9 * i)]
+    i64 = _pad64(cin_pad if cin_pad is not None else i)
+    w = w_oihw.new_zeros((o, 3, 3, i64))
+    w[..., :i] = w_oihw.permute(0, 2, 3, 1)
+    parts = [w.reshape(o, 9 * i64)]
     for s in skip_1x1:
-        parts.append(s.reshape(o, -1))
+        parts.append(_pad_k(s.reshape(o, -1)))
     return torch.cat(parts, dim=1).to(torch.float16).contiguous()
 
 
 def pack_conv3x3_padded(w_oihw: torch.Tensor, kpad: int) -> torch.Tensor:
-    """im2col variant: K = 9*I zero padded to `kpad` (multiple of 64)."""
+    """explicit-im2col variant (udt_im2col3x3_nhwc): K = 9*I (tap, channel) zero padded to `kpad` (multiple of 64)."""
     o, i, _, _ = w_oihw.shape
     out = torch.zeros((o, kpad), dtype=torch.float16, device=w_oihw.device)
     out[:, : 9 * i] = w_oihw.permute(0, 2, 3, 1).reshape(o, 9 * i).to(torch.float16)
@@ -29,8 +48,8 @@ def pack_conv3x3_padded(w_oihw: torch.Tensor, kpad: int) -> torch.Tensor:
 
 
 def pack_linear(w: torch.Tensor) -> torch.Tensor:
-    """[out, in] (or 1x1 conv [O, I, 1, 1]) -> fp16 [out, in]"""
-    return w.reshape(w.shape[0], -1).to(torch.float16).contiguous()
+    """[out, in] (or 1x1 conv [O, I, 1, 1]) -> fp16 [out, round_up(in, 64)]"""
+    return _pad_k(w.reshape(w.shape[0], -1)).to(torch.float16).contiguous()
 
 
 def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

@@ -94,15 +94,11 @@ class UNetB200:
         self.in_channels, self.out_channels, self.mc = in_channels, out_channels, model_channels
         self.t_context_dim = t_context_dim
         self.cin_pad = _round_up(in_channels, 8)
-        self.k_in = _round_up(9 * self.cin_pad, 64)
         emb_slices: list = []
         kv_slices: list = []
         hd = num_head_channels
 
-        w0 = sd["input_blocks.0.0.weight"].float()
-        wpad = torch.zeros((w0.shape[0], self.cin_pad, 3, 3))
-        wpad[:, :in_channels] = w0
-        self.w_conv_in = pack.pack_conv3x3_padded(wpad, self.k_in).to(dev)
+        self.w_conv_in = pack.pack_conv3x3(sd["input_blocks.0.0.weight"].float(), cin_pad=self.cin_pad).to(dev)
         self.b_conv_in = pack.f32(sd["input_blocks.0.0.bias"]).to(dev)
 
         # ---- mirror the constructor loops of openaimodel.py:352-536 to get the block plan
@@ -243,19 +239,14 @@ class UNetB200:
             elif kind == "st":
                 h = self._st(layer[1], h, kv, ctx_len, st_counter[0])
                 st_counter[0] += 1
-            elif kind == "down":  # conv3x3 stride 2 pad 1 (openaimodel.py:132-139) through im2col + GEMM
+            elif kind == "down":  # conv3x3 stride 2 pad 1 (openaimodel.py:132-139): strided TMA boxes
                 _, w, b, c = layer
-                nb, hh, ww, _ = h.shape
-                ho, wo = (hh + 1) // 2, (ww + 1) // 2
-                cols = ops.im2col3x3(h, 2, 1, ho, wo, 9 * c)
-                h = ops.linear(cols, w, b).view(nb, ho, wo, c)
+                h = ops.conv3x3(h, w, b, stride=2, pad=1)
             elif kind == "up":  # nearest x2 + conv3x3 (openaimodel.py:99-102)
                 _, w, b, c = layer
                 h = ops.conv3x3(ops.upsample2x(h), w, b)
-            elif kind == "conv_in":
-                nb, hh, ww, _ = h.shape
-                cols = ops.im2col3x3(h, 1, 1, hh, ww, self.k_in)
-                h = ops.linear(cols, self.w_conv_in, self.b_conv_in).view(nb, hh, ww, -1)
+            elif kind == "conv_in":  # Cin = 9 stored as 16 channels; TMA zero-fills each tap up to 64
+                h = ops.conv3x3(h, self.w_conv_in, self.b_conv_in)
         return h
 
     # ------------------------------------------------------------------------------------------ forward
