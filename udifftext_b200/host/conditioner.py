@@ -1,0 +1,210 @@
+"""GeneralConditioner and the three embedders of the UDiffText inference configuration.
+
+Reference: sgm/modules/encoders/modules.py:60-101 (AbstractEmbModel), :105-217 (GeneralConditioner), :800-860
+(SpatialRescaler), :999-1014 (LatentEncoder), :1088-1173 (LabelEncoder).  `get_unconditional_conditioning` keeps
+the reference's semantics and RNG draw order (posterior noise for `c` first, then for `uc`, both from the CPU
+generator) but recognises the shipped embedder triple and then runs the fused path: the masked-image encoder runs
+ONCE (its moments are identical for c and uc — only the posterior draw differs), the zeroed `uc` label embedding
+is not computed, and mask rescale + posterior sample + latent scale + concat are one kernel (K10).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .. import ops
+from . import rng
+from ..label import LabelEncoderB200
+from .config import instantiate_from_config
+from .network import _Component
+
+
+class AbstractEmbModel(_Component):
+    def __init__(self):
+        super().__init__()
+        self.is_trainable = False
+        self.ucg_rate = 0.0
+        self.input_key: Optional[str] = None
+        self.emb_key: Optional[str] = None
+        self.legacy_ucg_val = None
+
+    def _materialise(self, device):
+        pass
+
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)
+
+
+class LabelEncoder(AbstractEmbModel):
+    def __init__(self, max_len, emb_dim, n_heads=8, n_trans_layers=12, ckpt_path=None, trainable=False, **unused):
+        super().__init__()
+        if trainable:
+            raise NotImplementedError("LabelEncoder pre-training is out of scope (inference-only)")
+        self.max_len, self.emd_dim, self.n_heads, self.n_trans_layers = max_len, emb_dim, n_heads, n_trans_layers
+        self.exec: Optional[LabelEncoderB200] = None
+        if ckpt_path is not None:
+            sd = torch.load(ckpt_path, map_location="cpu", weights_only=False)["state_dict"]
+            self.load_weights(sd)
+
+    def _invalidate(self):
+        self.exec = None
+
+    def _materialise(self, device):
+        self.exec = LabelEncoderB200(self._require_weights(), device, self.max_len, self.emd_dim, self.n_heads,
+                                     self.n_trans_layers)
+
+    def forward(self, labels: Sequence[str]) -> torch.Tensor:
+        if self.exec is None:
+            raise RuntimeError("LabelEncoder: call .to(cuda device) after loading weights")
+        return self.exec(labels)
+
+
+class SpatialRescaler(AbstractEmbModel):
+    """1/8 bilinear rescale of the inpainting mask.  Only the shipped configuration (one bilinear stage, multiplier
+    0.125, no channel remap) is executable; it runs inside K10 on the fused path and stand-alone here."""
+
+    def __init__(self, n_stages=1, method="bilinear", multiplier=0.5, in_channels=3, out_channels=None, bias=False,
+                 wrap_video=False, kernel_size=1, remap_output=False):
+        super().__init__()
+        if n_stages != 1 or method != "bilinear" or multiplier != 0.125 or out_channels is not None or remap_output or wrap_video:
+            raise NotImplementedError("SpatialRescaler on B200: one bilinear stage with multiplier 0.125 only")
+        self.multiplier = multiplier
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        b, c, hh, ww = x.shape
+        assert c == 1
+        h, w = hh // 8, ww // 8
+        x = x.float().contiguous()
+        zeros_m = torch.zeros((b, h, w, 8), device=x.device, dtype=torch.float32)
+        zeros_n = torch.zeros((b, 4, h, w), device=x.device, dtype=torch.float32)
+        cat_c, _ = ops.vae_sample_pack(zeros_m, zeros_n, zeros_n, x, 1.0)
+        return cat_c[:, :1].contiguous()
+
+
+class LatentEncoder(AbstractEmbModel):
+    def __init__(self, scale_factor, config):
+        super().__init__()
+        self.scale_factor = scale_factor
+        cfg = dict(config)
+        params = dict(cfg.get("params", {}) or {})
+        params["part"] = "encoder"          # this instance only ever encodes (encoders/modules.py:1011-1014)
+        self.model = instantiate_from_config({"target": cfg["target"], "params": params})
+
+    def load_weights(self, sd):
+        self._sd = {}
+        self.model.load_weights({k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")})
+
+    def weights(self):
+        return {"model." + k: v for k, v in self.model.weights().items()}
+
+    def to(self, device):
+        self.model.to(device)
+        return self
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.scale_factor * self.model.encode(x)
+
+
+class GeneralConditioner:
+    OUTPUT_DIM2KEYS = {2: "vector", 3: "crossattn", 4: "concat", 5: "concat"}
+    KEY2CATDIM = {"vector": 1, "crossattn": 2, "concat": 1}
+
+    def __init__(self, emb_models: Sequence):
+        self.embedders: List[AbstractEmbModel] = []
+        for embconfig in emb_models:
+            embedder = instantiate_from_config(embconfig)
+            assert isinstance(embedder, AbstractEmbModel), \
+                f"embedder model {embedder.__class__.__name__} has to inherit from AbstractEmbModel"
+            embedder.is_trainable = embconfig.get("is_trainable", False)
+            embedder.ucg_rate = embconfig.get("ucg_rate", 0.0)
+            if "emb_key" in embconfig:
+                embedder.emb_key = embconfig["emb_key"]
+            if "input_key" in embconfig:
+                embedder.input_key = embconfig["input_key"]
+            else:
+                raise KeyError(f"need 'input_key' for embedder {embedder.__class__.__name__}")
+            embedder.legacy_ucg_val = embconfig.get("legacy_ucg_value", None)
+            if embedder.legacy_ucg_val is not None:
+                raise NotImplementedError("legacy_ucg_value (training-time conditioning dropout)")
+            self.embedders.append(embedder)
+
+    def to(self, device):
+        for e in self.embedders:
+            e.to(device)
+        return self
+
+    # -- generic path: mirrors GeneralConditioner.forward (encoders/modules.py:154-201) ----------------
+    def forward(self, batch: Dict, force_zero_embeddings: Optional[List] = None) -> Dict:
+        out: Dict[str, torch.Tensor] = {}
+        force_zero_embeddings = force_zero_embeddings or []
+        for e in self.embedders:
+            emb = e(batch[e.input_key])
+            key = e.emb_key if e.emb_key is not None else self.OUTPUT_DIM2KEYS[emb.dim()]
+            if e.ucg_rate > 0.0:
+                keep = torch.bernoulli((1.0 - e.ucg_rate) * torch.ones(emb.shape[0], device=emb.device))
+                emb = keep.view(-1, *([1] * (emb.dim() - 1))) * emb
+            if e.input_key in force_zero_embeddings:
+                emb = torch.zeros_like(emb)
+            out[key] = torch.cat((out[key], emb), self.KEY2CATDIM[key]) if key in out else emb
+        return out
+
+    __call__ = forward
+
+    def _fused_triple(self):
+        """(label, rescaler, latent) when the embedder list is exactly the shipped configuration, else None"""
+        if len(self.embedders) != 3:
+            return None
+        a, b, c = self.embedders
+        if isinstance(a, LabelEncoder) and isinstance(b, SpatialRescaler) and isinstance(c, LatentEncoder) \
+                and a.emb_key == "t_crossattn" and b.emb_key is None and c.emb_key is None:
+            return a, b, c
+        return None
+
+    def get_unconditional_conditioning(self, batch_c: Dict, batch_uc: Optional[Dict] = None,
+                                       force_uc_zero_embeddings: Optional[List] = None):
+        """encoders/modules.py:203-217"""
+        force = list(force_uc_zero_embeddings or [])
+        batch_uc = batch_c if batch_uc is None else batch_uc
+        saved = [e.ucg_rate for e in self.embedders]
+        for e in self.embedders:
+            e.ucg_rate = 0.0
+        try:
+            triple = self._fused_triple()
+            if triple is not None and self._same_images(batch_c, batch_uc, triple):
+                return self._fused(batch_c, batch_uc, force, *triple)
+            return self(batch_c), self(batch_uc, force)
+        finally:
+            for e, r in zip(self.embedders, saved):
+                e.ucg_rate = r
+
+    @staticmethod
+    def _same_images(batch_c, batch_uc, triple) -> bool:
+        _, resc, lat = triple
+        for key in (resc.input_key, lat.input_key):
+            a, b = batch_c[key], batch_uc[key]
+            if a is not b and (a.shape != b.shape or a.data_ptr() != b.data_ptr()) and not torch.equal(a, b):
+                return False
+        return True
+
+    def _fused(self, batch_c, batch_uc, force, label: LabelEncoder, resc: SpatialRescaler, lat: LatentEncoder):
+        dev = lat.model._exec().device
+        vae = lat.model._exec()
+        masked = batch_c[lat.input_key].to(dev)
+        mask = batch_c[resc.input_key].to(dev).float().contiguous()
+        moments = vae.encode_moments_nhwc(masked)                      # [B, h, w, 8] fp32, encoder runs once
+        b, h, w, _ = moments.shape
+        lat_shape = (b, vae.z_channels, h, w)
+        noise_c = rng.randn(lat_shape, dev)                            # RNG draw #1 (c), CPU generator
+        noise_uc = rng.randn(lat_shape, dev)                           # RNG draw #2 (uc)
+        cat_c, cat_uc = ops.vae_sample_pack(moments, noise_c, noise_uc, mask, lat.scale_factor)
+        emb_c = label(batch_c[label.input_key])
+        if label.input_key in force:
+            emb_uc = torch.zeros_like(emb_c)
+        else:
+            emb_uc = label(batch_uc[label.input_key])
+        if resc.input_key in force:
+            cat_uc[:, :1] = 0.0
+        if lat.input_key in force:
+            cat_uc[:, 1:] = 0.0
+        return {"t_crossattn": emb_c, "concat": cat_c}, {"t_crossattn": emb_uc, "concat": cat_uc}

@@ -1,0 +1,106 @@
+"""StepRunner — the B200-native execution of the sampler's hot loop.
+
+One denoising step of the reference (sampling.py:324-353) is: CFG batch doubling (guiders.py:31-40), sigma -> timestep
+quantisation + eps scaling (denoiser.py:22-28), concat wrapper (wrappers.py:27), the UNet, CFG combine
+(guiders.py:25-29) and the Euler update (sampling.py:349-351) — ~1.5 k eager library launches.  Here it is
+    udt_cfg_pack -> UNetB200.forward_nhwc (~640 launches of the hand-written kernels) -> udt_cfg_euler_step
+captured ONCE as a CUDA graph per (batch, latent size, context length) and replayed per step.  Everything that
+changes from step to step — the timestep-embedding bias rows of all 22 ResBlocks, c_in and the sigma increment — is
+precomputed for the whole schedule into a device table; a step copies its row into the static buffer the graph
+reads (one small D2D memcpy) and replays.  Step-invariant work (the `t_attn` K/V projections of the label
+embedding) is hoisted out of the loop.  No host synchronisation happens inside the loop.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .. import ops
+from ..unet import UNetB200
+from .schedule import DiscreteDenoiser, step_constants
+
+
+class StepRunner:
+    def __init__(self, unet: UNetB200, batch: int, h: int, w: int, ctx_len: int, cfg_scale: float, use_graph: bool = True):
+        self.unet, self.B, self.h, self.w, self.ctx_len = unet, batch, h, w, ctx_len
+        self.cfg_scale = float(cfg_scale)
+        self.use_graph = use_graph
+        dev = unet.device
+        self.device = dev
+        nb = 2 * batch
+        self.x = torch.zeros((batch, 4, h, w), device=dev, dtype=torch.float32)
+        self.cat_uc = torch.zeros((batch, 5, h, w), device=dev, dtype=torch.float32)
+        self.cat_c = torch.zeros_like(self.cat_uc)
+        self.kv = torch.zeros((nb * ctx_len, unet.kv_width), device=dev, dtype=torch.float16)
+        self.unet_in = torch.zeros((nb, h, w, unet.cin_pad_store), device=dev, dtype=torch.float16)
+        self.eps = torch.zeros((nb, h, w, unet.out_channels), device=dev, dtype=torch.float32)
+        # static per-step row: [emb_width rowbias | c_in | dsigma | pad]
+        self.row_width = (unet.emb_width + 2 + 3) // 4 * 4
+        self.row = torch.zeros((1, self.row_width), device=dev, dtype=torch.float32)
+        self.table: Optional[torch.Tensor] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------ per request
+    def begin(self, x: torch.Tensor, cond: Dict, uc: Dict, denoiser: DiscreteDenoiser, sigmas: torch.Tensor,
+              s_churn: float = 0.0, s_tmin: float = 0.0, s_tmax: float = float("inf")) -> None:
+        """load the request state into the static buffers and precompute the whole schedule's step table"""
+        u = self.unet
+        self.x.copy_(x)
+        self.cat_uc.copy_(uc["concat"])
+        self.cat_c.copy_(cond["concat"])
+        ctx = torch.cat([uc["t_crossattn"], cond["t_crossattn"]], dim=0)      # uc half first (guiders.py:36)
+        u.context_kv(ctx, out=self.kv)
+        k = step_constants(denoiser, sigmas, s_churn, s_tmin, s_tmax)
+        if float(k["gamma"].abs().max()) != 0.0:
+            raise NotImplementedError("s_churn > 0 (stochastic sampling) is not used by UDiffText (util.py:39)")
+        n = k["idx"].numel()
+        table = torch.zeros((n, self.row_width), device=self.device, dtype=torch.float32)
+        table[:, : u.emb_width] = u.temb_rowbias(k["idx"])
+        table[:, u.emb_width] = k["c_in"].to(self.device)
+        table[:, u.emb_width + 1] = (k["dsigma"] * k["eps_scale"]).to(self.device)
+        self.table = table
+        self.timesteps = k["idx"]
+
+    # ------------------------------------------------------------------------------------------ one step
+    def _body(self, export: bool = False) -> None:
+        u = self.unet
+        ew = u.emb_width
+        ops.cfg_pack(self.x, self.cat_uc, self.cat_c, self.row[0, ew: ew + 1], self.unet_in)
+        prev = u.export_attn_maps
+        u.export_attn_maps = export
+        try:
+            u.forward_nhwc(self.unet_in, self.row[:, :ew].expand(2 * self.B, ew), self.kv, self.ctx_len, out=self.eps)
+        finally:
+            u.export_attn_maps = prev
+        ops.cfg_euler_step_(self.x, self.eps, self.cfg_scale, self.row[0, ew + 1: ew + 2])
+
+    def _capture(self) -> None:
+        self._body()                       # warm-up: lazy one-time initialisation must not happen under capture
+        torch.cuda.synchronize(self.device)
+        x_saved = self.x.clone()
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g):
+            self._body()
+        self.launches_per_step = ops.launch_count() - n0
+        self.x.copy_(x_saved)
+        self.graph = g
+
+    def step(self, i: int, export_attn_maps: bool = False) -> None:
+        """advance the static state `self.x` by sampler step i"""
+        self.row.copy_(self.table[i: i + 1], non_blocking=True)
+        if export_attn_maps or not self.use_graph:
+            n0 = ops.launch_count()
+            self._body(export_attn_maps)
+            self.launches_per_step = ops.launch_count() - n0
+            return
+        if self.graph is None:
+            x_saved = self.x.clone()
+            self._capture()                # runs the body on the current row; state restored afterwards
+            self.x.copy_(x_saved)
+        self.graph.replay()
+
+    def result(self) -> torch.Tensor:
+        return self.x.clone()

@@ -14,7 +14,16 @@ from . import lib as _lib
 from .lib import UDT_ACT_GEGLU, UDT_ACT_NONE, UDT_ACT_RELU, UDT_ACT_SILU, GemmSrc, IGemmDesc  # noqa: F401
 
 
+_launches = 0  # C-ABI calls issued by this process (each is one or two kernel launches of libudt_b200)
+
+
+def launch_count() -> int:
+    return _launches
+
+
 def _stream() -> int:
+    global _launches
+    _launches += 1
     return torch.cuda.current_stream().cuda_stream
 
 

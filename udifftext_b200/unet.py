@@ -94,6 +94,7 @@ class UNetB200:
         self.in_channels, self.out_channels, self.mc = in_channels, out_channels, model_channels
         self.t_context_dim = t_context_dim
         self.cin_pad = _round_up(in_channels, 8)
+        self.cin_pad_store = 16  # udt_cfg_pack writes the 9-channel input as 16 fp16 channels (two 16-byte stores)
         emb_slices: list = []
         kv_slices: list = []
         hd = num_head_channels
@@ -187,11 +188,11 @@ class UNetB200:
         e = ops.linear(h, self.w_te2, self.b_te2, act=ops.UDT_ACT_SILU)  # SiLU of emb_layers[0] fused here
         return ops.linear(e, self.w_emb, self.b_emb, out_fp32=True)
 
-    def context_kv(self, t_context: torch.Tensor) -> torch.Tensor:
+    def context_kv(self, t_context: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[NB, L, t_context_dim] fp32 -> fp16 [NB*L, kv_width]: to_k/to_v of every t_attn layer (attention.py:144-145)."""
         nb, l, d = t_context.shape
         ctx = t_context.to(self.device).reshape(nb * l, d).half().contiguous()
-        return ops.linear(ctx, self.w_kv)
+        return ops.linear(ctx, self.w_kv, out=out)
 
     def _res(self, r: _Res, x0: torch.Tensor, x1: Optional[torch.Tensor], rowbias: torch.Tensor) -> torch.Tensor:
         nb = x0.shape[0]
