@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — 512x512, 50-step DDIM images/sec of the UDiffText inference hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              our arm: hand-written sm_100a kernels
+  python bench.py --impl reference [--gpus N --steps K --warmup W]  the reference's CPU path (oracle port) on the host cores
+  torchrun ... bench.py --gpus N ...                               one rank per GPU, batch sharded, one NCCL all-gather
+
+A "step" is one full `predict()` (test.py:19-40) over one batch: conditioner (LabelEncoder, mask rescale, VAE encode,
+posterior sample) -> 50 CFG-doubled UNet + Euler steps -> VAE decode -> clamp.  Workload = BASELINE.json configs[1]:
+batch 4 per GPU, 512x512, 50 steps, 8-character strings, synthetic inputs, seeded random weights of the exact
+architecture (no checkpoints / datasets exist offline).  `value` times the path with the request tensors already
+resident in HBM; `e2e` times the same call from pinned host buffers to host images (H2D + D2H inside the timed
+region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+IMG = 512
+DDIM_STEPS = 50
+LABEL_LEN = 8
+PER_GPU_BATCH = 4
+# SURVEY.md §8(d) / BASELINE.md §2: algorithmic FLOPs measured on the unmodified reference module graph
+GFLOP_UNET_SAMPLE_FWD = 798.66
+GFLOP_UNET_IGEMM = 394.78 + 5.66 + 18.04 + 257.14   # conv3x3 + conv3x3-s2 + conv1x1 + linear: the udt_igemm share
+GFLOP_VAE_ENC, GFLOP_VAE_DEC = 1116.7, 2514.5
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))),
+                "tflops_burst": float(p.get("bf16_tflops", 1590.0)), "hbm_gbs": float(p.get("hbm_gbs", 6650.0)),
+                "source": "measured"}
+    return {"tflops": 1590.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md: 1.59 PFLOP/s, 6.65 TB/s)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)"""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(r[2 + j].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# =================================================================================================== reference arm
+def cpu_reference_sample(threads: int):
+    """The reference's algorithm for this path on the host cores: oracle/restated.py (the fp32 PyTorch restatement
+    pinned against the unmodified reference by oracle/make_golden.py; /root/reference itself does not exist on the
+    GPU box).  Bounded sample of the workload: for ONE 512x512 image the conditioner's VAE encode, ONE CFG-doubled
+    UNet evaluation and the VAE decode are timed; images/s for 50 steps = 1 / (t_enc + 50 t_unet + t_dec)
+    (the reference runs the encoder twice per image — c and uc — so 2 t_enc is charged)."""
+    import torch
+    from oracle import restated as R
+    from udifftext_b200 import synth
+    torch.set_num_threads(threads)
+    man = synth.load_manifest("full")
+    sd = synth.synthetic_state_dict(man, 1234)
+    unet_sd = R._sub(sd, "model.diffusion_model.")
+    enc_sd = R._sub(sd, "conditioner.embedders.2.model.")
+    dec_sd = R._sub(sd, "first_stage_model.")
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        x = torch.randn((2, 9, IMG // 8, IMG // 8), generator=g)
+        ctx = torch.randn((2, 12, 2048), generator=g)
+        t0 = time.perf_counter()
+        R.unet_forward(unet_sd, x, torch.tensor([999, 999]), ctx)
+        t_unet = time.perf_counter() - t0
+        img = torch.rand((1, 3, IMG, IMG), generator=g) * 2 - 1
+        t0 = time.perf_counter()
+        R.vae_encode_moments(enc_sd, img)
+        t_enc = time.perf_counter() - t0
+        z = torch.randn((1, 4, IMG // 8, IMG // 8), generator=g)
+        t0 = time.perf_counter()
+        R.vae_decode(dec_sd, z)
+        t_dec = time.perf_counter() - t0
+    per_image = 2 * t_enc + DDIM_STEPS * t_unet + t_dec
+    return {"value": 1.0 / per_image, "t_unet_cfg_s": t_unet, "t_enc_s": t_enc, "t_dec_s": t_dec, "seconds_per_image": per_image}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        vals.append(cpu_reference_sample(threads))
+    timed = vals[args.warmup:] if len(vals) > args.warmup else vals
+    v = sum(t["value"] for t in timed) / len(timed)
+    sample = ("1 image 512x512: VAE encode (x2) + one CFG UNet evaluation (batch 2) + VAE decode timed on the host; "
+              "images/s = 1/(2 t_enc + 50 t_unet + t_dec)")
+    line = {"impl": "reference", "metric": "512x512 50-step DDIM images/sec", "value": v, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * PER_GPU_BATCH / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch {PER_GPU_BATCH}, {IMG}x{IMG}, {DDIM_STEPS} DDIM steps, {LABEL_LEN}-char strings (BASELINE configs[1])",
+                       "note": "reference algorithm (fp32 PyTorch restatement, oracle/restated.py) on host CPU cores"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+                             "detail": timed[-1]},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# =================================================================================================== our arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from udifftext_b200 import api, ops, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — udifftext_b200 has no CPU path")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    gb = B * world
+
+    model = api.build_engine("full", dev)
+    cfgs = api.runtime_config(steps=DDIM_STEPS, batch_size=B, gpu=local, noise_iters=0)
+    sampler = api.init_sampling(cfgs)
+    sampler.verbose = False
+
+    # global synthetic request (seeded), this rank's rows; pinned host copies for the e2e leg
+    full = synth.synthetic_batch(2, gb, IMG, IMG, LABEL_LEN)
+    lo, hi = rank * B, (rank + 1) * B
+
+    def shard_rows(pin: bool):
+        out = {}
+        for k, v in full.items():
+            if isinstance(v, torch.Tensor):
+                t = v[lo:hi].contiguous()
+                out[k] = t.pin_memory() if pin else t
+            elif isinstance(v, list):
+                out[k] = v[lo:hi]
+            else:
+                out[k] = v
+        return out
+
+    host_batch = shard_rows(pin=True)
+    dev_batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_batch.values() if isinstance(v, torch.Tensor))
+    gathered = torch.empty((gb, 3, IMG, IMG), device=dev, dtype=torch.float32) if world > 1 else None
+    host_out = torch.empty((gb if world > 1 else B, 3, IMG, IMG), dtype=torch.float32).pin_memory()
+    d2h = host_out.numel() * 4
+
+    def one_request(batch, seed, to_host: bool):
+        torch.manual_seed(seed)
+        img, _ = api.predict(cfgs, model, sampler, dict(batch), shard=(gb, lo, hi))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, img.contiguous())   # the path's one collective
+            img = gathered
+        if to_host:
+            host_out.copy_(img, non_blocking=True)
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(batch, to_host: bool):
+        for i in range(args.warmup):
+            one_request(batch, 100 + i, to_host)
+        barrier()
+        c0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        e0.record()
+        for i in range(args.steps):
+            one_request(batch, 200 + i, to_host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ck = clocks.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ck, ops.launch_count() - c0
+
+    ms_dev, clocks, eager_calls = timed(dev_batch, to_host=False)
+    ms_e2e, clocks_e2e, _ = timed(host_batch, to_host=True)
+
+    runner = sampler.last_runner
+    # kernels launched in the timed region: graph replays (captured launches per step) + eager conditioner/decoder calls
+    launches = eager_calls + args.steps * DDIM_STEPS * max(runner.launches_per_step, 1) - args.steps * DDIM_STEPS * 0
+    # ---- per-kernel-class timing of ONE UNet CFG step, live, CUDA events on the launching stream (eager replay)
+    prof = ops.profile_step(runner, warm=2, reps=3)
+    peaks = measured_peaks()
+    ig = prof["by_op"].get("udt_igemm", {"ms": 0.0, "calls": 0})
+    unet_step_ms = prof["step_ms_graph"]
+    roofline = None
+    if ig["ms"] > 0:
+        flops = 2 * B * GFLOP_UNET_IGEMM * 1e9            # algorithmic FLOPs of all igemm launches of one CFG step
+        ach = flops / (ig["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "udt_igemm_kernel", "achieved": ach, "peak": peaks["tflops"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                    "launches_per_unet_step": ig["calls"], "ms_per_unet_step": ig["ms"],
+                    "share_of_step": ig["ms"] / max(prof["step_ms_eager_sum"], 1e-9)}
+
+    line = None
+    if rank == 0:
+        imgs = gb * args.steps
+        value = imgs / (ms_dev * 1e-3)
+        e2e = imgs / (ms_e2e * 1e-3)
+        line = {"metric": "512x512 50-step DDIM images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": f"batch {B} per GPU, {IMG}x{IMG}, {DDIM_STEPS} DDIM steps (EulerEDM+LegacyDDPM, CFG 5.0), "
+                                       f"{LABEL_LEN}-char strings, noise_iters 0 (BASELINE configs[1])",
+                           "global_batch": gb, "parallelism": f"batch-sharded x{world}, one all-gather of decoded images",
+                           "l2": "working set per step >> 126 MB L2 (1.78 GB fp16 UNet weights streamed every step); no explicit flush",
+                           "weights": "seeded synthetic, exact SD-2-inpainting UNifiedUNet / AutoencoderKL / LabelEncoder architecture"},
+                "unet_step_ms": unet_step_ms,
+                "unet_step_tflops": 2 * B * GFLOP_UNET_SAMPLE_FWD / unet_step_ms if unet_step_ms else None,
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "clocks": clocks, "clocks_e2e": clocks_e2e,
+                "roofline": roofline,
+                "kernel_breakdown_unet_step": prof["by_op"]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        s = cpu_reference_sample(threads)
+        line["cpu_baseline"] = {"value": s["value"], "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": "1 image 512x512 on the host cores via oracle/restated.py: VAE encode (x2) + one CFG UNet "
+                                          "evaluation (batch 2) + VAE decode; images/s = 1/(2 t_enc + 50 t_unet + t_dec)",
+                                "detail": s}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per request")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus != world and world == 1 and args.gpus > 1:
+            # convenience: python bench.py --gpus N re-launches itself under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,7 +32,7 @@ extern "C" {
 #define UDT_ACT_GEGLU 2 /* out[:, j] = x_j * gelu_erf(gate_j); weight rows interleaved per column tile */
 #define UDT_ACT_RELU 3
 
-int udt_version(void);            /* ABI version (1) */
+int udt_version(void);            /* ABI version (2) */
 int udt_arch(void);               /* compute capability of the current device *10 (100 on B200); <0 on error */
 const char* udt_last_error(void); /* thread-local message of the last failing call */
 int udt_num_sms(void);

@@ -87,7 +87,8 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* m, const void* ptr, uint32_t rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box, const cuuint32_t* estr_in = nullptr) {
+                  const cuuint32_t* box, const cuuint32_t* estr_in = nullptr,
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return fail(UDT_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(UDT_ERR_ALIGN, "TMA base pointer not 16-byte aligned");
@@ -95,7 +96,7 @@ static int encode(CUtensorMap* m, const void* ptr, uint32_t rank, const cuuint64
   if (estr_in != nullptr)
     for (uint32_t i = 0; i < rank; ++i) estr[i] = estr_in[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(UDT_ERR_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d; rank %u dims %llu,%llu box %u,%u)", (int)r,
@@ -123,10 +124,20 @@ int make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint
   return encode(m, ptr, 4, dims, strides, box, estr);
 }
 
+// epilogue tile map: {32 channels, bw, bh, bn} boxes of an NHWC fp16 tensor with the 64B swizzle (rows of 64 B)
+int make_tmap_nhwc_c32(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld,
+                       uint32_t bw, uint32_t bh, uint32_t bn) {
+  if ((ld * 2) % 16 != 0) return fail(UDT_ERR_ALIGN, "channel pitch %llu elements is not a multiple of 8", (unsigned long long)ld);
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {ld * 2, ld * 2 * W, ld * 2 * W * H};
+  cuuint32_t box[4] = {32, bw, bh, bn};
+  return encode(m, ptr, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 }  // namespace udt_host
 
 extern "C" {
-int udt_version(void) { return 1; }
+int udt_version(void) { return 2; }
 int udt_arch(void) { return udt_host::arch(); }
 const char* udt_last_error(void) { return udt_host::error_buffer(); }
 int udt_num_sms(void) { return udt_host::num_sms(); }

@@ -26,4 +26,8 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, 
 int make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld,
                    uint32_t bw, uint32_t bh, uint32_t bn, uint32_t pix_stride);
 
+// epilogue tile map: {32 channels, bw, bh, bn} boxes, 64B swizzle (TMA store of finished tiles / residual prefetch)
+int make_tmap_nhwc_c32(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld,
+                       uint32_t bw, uint32_t bh, uint32_t bn);
+
 }  // namespace udt_host

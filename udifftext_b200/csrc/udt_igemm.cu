@@ -8,9 +8,13 @@
 //                                2-D box load {64, BN} of the K-major fp16 weights, both 128B-swizzled.
 //   warp 1      MMA issuer     : tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16, fp32 accumulators
 //                                in TMEM, two accumulator buffers so the epilogue of tile i overlaps tile i+1.
-//   warps 2..5  epilogue       : tcgen05.ld (thread = output row), bias / per-image bias / SiLU / GEGLU /
-//                                residual, fp16 (or fp32) stores straight to global memory.
-// Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+//   warps 2..5  epilogue       : tcgen05.ld (thread = output row), bias / per-image bias / SiLU / ReLU / GEGLU /
+//                                residual.  fp16 outputs are staged: 32-column chunks go registers -> 64B-swizzled
+//                                shared memory -> TMA tile store (coalesced, clipped at the tensor edge), the
+//                                residual chunks are TMA-prefetched two chunks ahead (across tile boundaries) and
+//                                the bias row is staged in shared memory once per tile.  Tiny / fp32 outputs
+//                                (N_out < 8, out_fp32, BN = 16) use direct global stores.
+// Pipelines: smem full/empty mbarrier ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), residual full.
 //
 // Replaces the cuDNN / cuBLAS call sites listed in include/udt_api.h (udt_igemm).
 #include "udt_common.cuh"
@@ -30,6 +34,12 @@ constexpr int kAccStride = 256;                     // TMEM column offset of the
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kCtrlBytes = 1024;
 constexpr int kGegluTile = 128;
+constexpr int kChunkCols = 32;                      // epilogue staging granularity: 32 fp16 columns = 64 B rows
+constexpr int kChunkBytes = kBlockM * kChunkCols * 2;  // 8 KB
+constexpr int kBiasImgs = 4;                        // per-image bias rows staged per tile (tiles spanning more images
+                                                    // read rowbias from global memory)
+constexpr int kBiasBytes = kBiasImgs * 256 * 4;     // 4 KB
+constexpr int kEpiBarrier = 1;                      // named barrier id of the 4 epilogue warps
 
 struct IGemmParams {
   CUtensorMap mapA[3];
@@ -49,6 +59,9 @@ struct IGemmParams {
   int32_t ldr, ld_rowbias;
   void* out;
   int32_t ldo, out_fp32, act;
+  int32_t staged;        // 1: smem-staged epilogue with TMA store (fp16 out), 0: direct global stores
+  CUtensorMap mapOut;    // staged mode: {32, bw, bh, bn} boxes of the output tensor, 64B swizzle
+  CUtensorMap mapRes;    // staged mode with residual: same boxes of the residual tensor
 };
 
 struct TileCoord {
@@ -144,12 +157,20 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+
+  // staged epilogue buffers sit between the control block and the operand ring
+  const bool has_res_stage = p.staged && p.residual != nullptr;
+  const int epi_bytes = p.staged ? (2 * kChunkBytes + (has_res_stage ? 2 * kChunkBytes : 0) + kBiasBytes) : 0;
+  uint8_t* sOut = base + kCtrlBytes;
+  uint8_t* sRes = sOut + 2 * kChunkBytes;
+  float* sBias = reinterpret_cast<float*>(sOut + 2 * kChunkBytes + (has_res_stage ? 2 * kChunkBytes : 0));
 
   const int b_bytes = p.BN * kBlockK * 2;
-  uint8_t* sA = base + kCtrlBytes;
+  uint8_t* sA = base + kCtrlBytes + epi_bytes;
   uint8_t* sB = sA + p.stages * kABytes;
-  const uint32_t sA_addr = base_addr + kCtrlBytes;
+  const uint32_t sA_addr = base_addr + kCtrlBytes + epi_bytes;
   const uint32_t sB_addr = sA_addr + p.stages * kABytes;
 
   const int warp = threadIdx.x >> 5;
@@ -165,6 +186,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);
+      mbar_init(&res_full[s], 1);
+    }
+    if (p.staged) {
+      tma_prefetch_desc(&p.mapOut);
+      if (p.residual != nullptr) tma_prefetch_desc(&p.mapRes);
     }
     fence_mbar_init();
   }
@@ -238,8 +264,177 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
         if (as == 0) aphase ^= 1u;
       }
     }
+  } else if (p.staged) {
+    // ------------------------------------------------------------------ staged epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int row = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;             // 0..127 within the epilogue group
+    const bool leader = (et == 0);               // issues the TMA stores / residual prefetches
+    const bool geglu = (p.act == UDT_ACT_GEGLU);
+    const int cols_per_tile = geglu ? p.BN / 2 : p.BN;     // logical output columns per tile
+    const int nchunks = cols_per_tile / kChunkCols;
+    const int n_logical = geglu ? p.N_out / 2 : p.N_out;
+    const int bwh = p.bw * p.bh;
+    const int img_in_tile = row / bwh;           // which of the tile's images this row belongs to
+    const bool bias_staged_rb = (p.rowbias == nullptr) || (p.bn <= kBiasImgs);
+    const uint32_t swz = static_cast<uint32_t>((row >> 1) & 3);
+    uint8_t* my_out_row0 = sOut + row * 64;
+    const uint8_t* my_res_row0 = sRes + row * 64;
+
+    // residual prefetch cursor: runs two chunks ahead of the consumer, across tile boundaries
+    int pf_tile = blockIdx.x, pf_chunk = 0;
+    uint32_t pf_count = 0;
+    auto prefetch_residual = [&]() {
+      if (pf_tile >= p.num_tiles) return;
+      const TileCoord t = decode_tile(p, pf_tile);
+      const int col = t.n_blk * cols_per_tile + pf_chunk * kChunkCols;
+      const int b = pf_count & 1;
+      mbar_expect_tx(&res_full[b], kChunkBytes);
+      tma_load_4d(&p.mapRes, &res_full[b], sRes + b * kChunkBytes, col, t.w0, t.h0, t.n0);
+      ++pf_count;
+      if (++pf_chunk == nchunks) {
+        pf_chunk = 0;
+        pf_tile += gridDim.x;
+      }
+    };
+    if (has_res_stage && leader) {
+      prefetch_residual();
+      prefetch_residual();
+    }
+
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t g = 0;  // global chunk counter of this CTA (buffer = g & 1)
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int col_tile = tc.n_blk * cols_per_tile;
+      // ---- stage bias (+ per-image bias) of this tile's columns: global loads fly while the MMAs finish
+      float bv[2][kBiasImgs];
+      const int nimg = (p.rowbias != nullptr && bias_staged_rb) ? min(p.bn, kBiasImgs) : 1;
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int cc = et + h2 * 128;              // column within the (packed) tile, < BN <= 256
+        const int gcol = tc.n_blk * p.BN + cc;
+        const bool ok = (cc < p.BN) && (gcol < p.N_out);
+        const float b0 = (ok && p.bias != nullptr) ? __ldg(p.bias + gcol) : 0.0f;
+#pragma unroll
+        for (int im = 0; im < kBiasImgs; ++im) {
+          float v = b0;
+          if (ok && im < nimg && p.rowbias != nullptr && bias_staged_rb) {
+            const int img = min(tc.n0 + im, p.NB - 1);
+            v += __ldg(p.rowbias + static_cast<size_t>(img) * p.ld_rowbias + gcol);
+          }
+          bv[h2][im] = v;
+        }
+      }
+      named_bar_sync(kEpiBarrier, 128);            // previous tile's readers of sBias are done
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int cc = et + h2 * 128;
+        if (cc < p.BN) {
+#pragma unroll
+          for (int im = 0; im < kBiasImgs; ++im)
+            if (im < nimg) sBias[im * 256 + cc] = bv[h2][im];
+        }
+      }
+      named_bar_sync(kEpiBarrier, 128);
+      const float* my_bias = sBias + ((p.rowbias != nullptr && bias_staged_rb) ? min(img_in_tile, kBiasImgs - 1) * 256 : 0);
+      const int my_img = min(tc.n0 + img_in_tile, p.NB - 1);
+
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        const int b = g & 1;
+        const int c0 = c * kChunkCols;
+        float f[32];
+        if (geglu) {
+          uint32_t vx[32], vg[32];
+          tmem_ld32(taddr + c0, vx);
+          tmem_ld32(taddr + p.BN / 2 + c0, vg);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(vx[j]) + my_bias[c0 + j];
+            const float gt = __uint_as_float(vg[j]) + my_bias[p.BN / 2 + c0 + j];
+            f[j] = x * gelu_erf_f(gt);
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(my_bias + c0 + j);
+            f[j] = __uint_as_float(v[j]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (!bias_staged_rb) {
+            const float* rb = p.rowbias + static_cast<size_t>(my_img) * p.ld_rowbias + col_tile + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col_tile + c0 + j < p.N_out) f[j] += __ldg(rb + j);
+          }
+          if (p.act == UDT_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+          } else if (p.act == UDT_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+        }
+        if (c == nchunks - 1) {                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        if (has_res_stage) {
+          mbar_wait(&res_full[b], (g >> 1) & 1);
+          const uint8_t* rrow = my_res_row0 + b * kChunkBytes;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rrow + ((static_cast<uint32_t>(q) ^ swz) << 4));
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 rf = __half22float2(rh[j]);
+              f[q * 8 + 2 * j] += rf.x;
+              f[q * 8 + 2 * j + 1] += rf.y;
+            }
+          }
+        }
+        // the TMA store that last used sOut[b] (two chunks ago) must have finished reading it
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(kEpiBarrier, 128);
+        uint8_t* orow = my_out_row0 + b * kChunkBytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 ov;
+          ov.x = pack_half2(f[q * 8 + 0], f[q * 8 + 1]);
+          ov.y = pack_half2(f[q * 8 + 2], f[q * 8 + 3]);
+          ov.z = pack_half2(f[q * 8 + 4], f[q * 8 + 5]);
+          ov.w = pack_half2(f[q * 8 + 6], f[q * 8 + 7]);
+          *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(q) ^ swz) << 4)) = ov;
+        }
+        fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(kEpiBarrier, 128);          // chunk complete in sOut[b]; sRes[b] fully consumed
+        if (leader) {
+          const int col = col_tile + c0;
+          if (col < n_logical) {
+            tma_store_4d(&p.mapOut, sOut + b * kChunkBytes, col, tc.w0, tc.h0, tc.n0);
+          }
+          tma_store_commit();
+          if (has_res_stage) prefetch_residual();  // refill sRes[b] with the chunk two ahead
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+    if (leader) tma_store_wait_all<0>();           // all output tiles written before the CTA retires
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ direct epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
     const int row = quarter * 32 + lane;
     const int bwh = p.bw * p.bh;
@@ -457,8 +652,24 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
                     static_cast<uint64_t>(ldw), 64, static_cast<uint32_t>(BN));
   if (rc != UDT_OK) return rc;
 
+  // staged (TMA store) epilogue for fp16 outputs with a TMA-compatible layout; tiny / fp32 outputs store directly
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && (d->ldo % 8 == 0) &&
+                         (d->residual == nullptr || (((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && d->ldr % 8 == 0));
+  const int n_logical = act == UDT_ACT_GEGLU ? N_out / 2 : N_out;
+  p.staged = (!d->out_fp32 && BN >= 32 && aligned16 && n_logical >= 8) ? 1 : 0;
+  int epi_bytes = 0;
+  if (p.staged) {
+    rc = make_tmap_nhwc_c32(&p.mapOut, d->out, static_cast<uint64_t>(n_logical), W, H, NB, d->ldo, p.bw, p.bh, p.bn);
+    if (rc != UDT_OK) return rc;
+    epi_bytes = 2 * kChunkBytes + kBiasBytes;
+    if (d->residual != nullptr) {
+      rc = make_tmap_nhwc_c32(&p.mapRes, d->residual, static_cast<uint64_t>(n_logical), W, H, NB, d->ldr, p.bw, p.bh, p.bn);
+      if (rc != UDT_OK) return rc;
+      epi_bytes += 2 * kChunkBytes;
+    }
+  }
   const int stage_bytes = kABytes + BN * kBlockK * 2;
-  int stages = (kSmemBudget - kCtrlBytes - 1024) / stage_bytes;
+  int stages = (kSmemBudget - kCtrlBytes - 1024 - epi_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(UDT_ERR_SHAPE, "udt_igemm: tile does not fit shared memory");
   p.stages = stages;
@@ -472,7 +683,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   p.out_fp32 = d->out_fp32;
   p.act = act;
 
-  const int smem = kCtrlBytes + 1024 + stages * stage_bytes;
+  const int smem = kCtrlBytes + 1024 + epi_bytes + stages * stage_bytes;
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   udt_igemm_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("udt_igemm");

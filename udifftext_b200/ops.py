@@ -14,7 +14,9 @@ from . import lib as _lib
 from .lib import UDT_ACT_GEGLU, UDT_ACT_NONE, UDT_ACT_RELU, UDT_ACT_SILU, GemmSrc, IGemmDesc  # noqa: F401
 
 
-_launches = 0  # C-ABI calls issued by this process (each is one or two kernel launches of libudt_b200)
+_launches = 0   # C-ABI compute calls issued by this process (each is one or two kernel launches of libudt_b200)
+SHAPE_LOG = None  # when a list: one problem-shape tuple per call (scripts/profile_unet_step.py)
+_prof = None    # when a list: (entry point, start event, end event) per call — see profile_step()
 
 
 def launch_count() -> int:
@@ -22,9 +24,68 @@ def launch_count() -> int:
 
 
 def _stream() -> int:
-    global _launches
-    _launches += 1
     return torch.cuda.current_stream().cuda_stream
+
+
+def _invoke(name: str, *args, shape=None) -> None:
+    """call one C-ABI entry point on torch's current stream; raises UdtError on a non-zero return code"""
+    global _launches
+    if SHAPE_LOG is not None:
+        SHAPE_LOG.append(shape if shape is not None else tuple(a for a in args if isinstance(a, int) and a < (1 << 24)))
+    fn = getattr(_lib.load(), name)
+    _launches += 1
+    if _prof is None:
+        rc = fn(*args, _stream())
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, _stream())
+        e1.record()
+        _prof.append((name, e0, e1))
+    _lib.check(rc, name)
+
+
+def profile_step(runner, warm: int = 2, reps: int = 3) -> dict:
+    """Live per-entry-point device time of ONE sampler step (udt_cfg_pack -> UNet -> udt_cfg_euler_step), measured
+    with CUDA events on the launching stream around every C-ABI call of an eager (un-graphed) replay, plus the
+    duration of the same step as a CUDA-graph replay.  The runner's state is restored afterwards."""
+    global _prof
+    x_saved = runner.x.clone()
+    runner.row.copy_(runner.table[0:1])
+    for _ in range(warm):
+        runner._body()
+    torch.cuda.synchronize()
+    acc: dict = {}
+    total = 0.0
+    for _ in range(reps):
+        _prof = []
+        try:
+            runner._body()
+            torch.cuda.synchronize()
+            for name, e0, e1 in _prof:
+                ms = e0.elapsed_time(e1)
+                a = acc.setdefault(name, {"ms": 0.0, "calls": 0})
+                a["ms"] += ms / reps
+                a["calls"] += 1
+                total += ms / reps
+        finally:
+            _prof = None
+    for a in acc.values():
+        a["calls"] //= reps
+    step_ms_graph = None
+    if runner.graph is not None:
+        for _ in range(warm):
+            runner.graph.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            runner.graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms_graph = e0.elapsed_time(e1) / reps
+    runner.x.copy_(x_saved)
+    return {"by_op": acc, "step_ms_eager_sum": total, "step_ms_graph": step_ms_graph}
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -55,7 +116,6 @@ def igemm(
 ) -> torch.Tensor:
     """Segmented implicit GEMM (udt_igemm).  `srcs` = [(tensor, C, ld, taps[, stride, pad, H_in, W_in]), ...];
     (nb, h, w) are the OUTPUT pixel dims; 3x3 segments default to stride 1 / pad 1."""
-    L = _lib.load()
     d = IGemmDesc()
     for i, src in enumerate(srcs):
         t, c, ld, taps = src[:4]
@@ -71,7 +131,12 @@ def igemm(
     d.ld_rowbias = 0 if rowbias is None else (n_out if ld_rowbias is None else ld_rowbias)
     d.residual, d.ldr = _ptr(residual), ldr
     d.out, d.ldo, d.out_fp32, d.act, d.bn_hint = out.data_ptr(), ldo, int(out_fp32), act, bn_hint
-    _lib.check(L.udt_igemm(ctypes.byref(d), _stream()), "udt_igemm")
+    if SHAPE_LOG is not None:
+        k = sum(src[3] * ((src[1] + 63) // 64 * 64) for src in srcs)
+        tag = "+".join(f"{src[3]}x{src[1]}" + (f"s{src[4]}" if len(src) > 4 and src[4] != 1 else "") for src in srcs)
+        _invoke("udt_igemm", ctypes.byref(d), shape=(nb * h * w, n_out, k, tag, f"{nb}x{h}x{w}", act))
+        return out
+    _invoke("udt_igemm", ctypes.byref(d))
     return out
 
 
@@ -117,7 +182,6 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
               x1: Optional[torch.Tensor] = None, groups: int = 32, out: Optional[torch.Tensor] = None,
               ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GroupNorm(+SiLU) over NHWC fp16; with `x1` normalises cat([x0, x1], channel) and writes the concat."""
-    L = _lib.load()
     nb = x0.shape[0]
     c0 = x0.shape[-1]
     c1 = 0 if x1 is None else x1.shape[-1]
@@ -126,160 +190,137 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
         out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.float16)
     if ws is None or ws.numel() * 8 < groupnorm_ws_bytes(nb, hw, c0 + c1, groups):
         ws = torch.empty(groupnorm_ws_bytes(nb, hw, c0 + c1, groups) // 8, device=x0.device, dtype=torch.float64)
-    rc = L.udt_groupnorm_nhwc(x0.data_ptr(), c0, _ptr(x1), c1, out.data_ptr(), nb, hw, groups, gamma.data_ptr(),
-                              beta.data_ptr(), float(eps), int(silu), ws.data_ptr(), _stream())
-    _lib.check(rc, "udt_groupnorm_nhwc")
+    _invoke("udt_groupnorm_nhwc", x0.data_ptr(), c0, _ptr(x1), c1, out.data_ptr(), nb, hw, groups, gamma.data_ptr(),
+                              beta.data_ptr(), float(eps), int(silu), ws.data_ptr())
     return out
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    L = _lib.load()
     c = x.shape[-1]
     rows = x.numel() // c
     if out is None:
         out = torch.empty_like(x)
-    rc = L.udt_layernorm(x.data_ptr(), out.data_ptr(), rows, c, gamma.data_ptr(), beta.data_ptr(), float(eps), _stream())
-    _lib.check(rc, "udt_layernorm")
+    _invoke("udt_layernorm", x.data_ptr(), out.data_ptr(), rows, c, gamma.data_ptr(), beta.data_ptr(), float(eps))
     return out
 
 
 def fmha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, nq: int, nkv: int, heads: int, scale: float,
          out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q/k/v: 2-D fp16 views [B*N, >= heads*64] (may be column slices of one fused QKV buffer)."""
-    L = _lib.load()
     if out is None:
         out = torch.empty((b * nq, heads * 64), device=q.device, dtype=torch.float16)
-    rc = L.udt_fmha_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, nq, nkv, heads, q.stride(0),
-                        k.stride(0), v.stride(0), out.stride(0), float(scale), _stream())
-    _lib.check(rc, "udt_fmha_fwd")
+    _invoke("udt_fmha_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, nq, nkv, heads, q.stride(0),
+                        k.stride(0), v.stride(0), out.stride(0), float(scale))
     return out
 
 
 def xattn_small_l(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, b: int, n: int, l: int, heads: int,
                   scale: float, out: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [B*N, heads*64]; kc/vc [B*L, heads*64] (row pitch may be larger); probs fp32 [B*heads, N, L] optional."""
-    L = _lib.load()
     if out is None:
         out = torch.empty((b * n, heads * 64), device=q.device, dtype=torch.float16)
-    rc = L.udt_xattn_small_l(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), out.data_ptr(), _ptr(probs), b, n, l, heads,
-                             q.stride(0), kc.stride(0), out.stride(0), float(scale), _stream())
-    _lib.check(rc, "udt_xattn_small_l")
+    _invoke("udt_xattn_small_l", q.data_ptr(), kc.data_ptr(), vc.data_ptr(), out.data_ptr(), _ptr(probs), b, n, l, heads,
+                             q.stride(0), kc.stride(0), out.stride(0), float(scale))
     return out
 
 
 def label_embed(idx: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
     """idx int32 [B, L]; emb fp32 [V, D]; pe fp32 [L, D] -> fp16 [B*L, D]"""
-    L = _lib.load()
     b, l = idx.shape
     d = emb.shape[1]
     out = torch.empty((b * l, d), device=emb.device, dtype=torch.float16)
-    _lib.check(L.udt_label_embed(idx.data_ptr(), emb.data_ptr(), pe.data_ptr(), out.data_ptr(), b * l, l, d, _stream()),
-               "udt_label_embed")
+    _invoke("udt_label_embed", idx.data_ptr(), emb.data_ptr(), pe.data_ptr(), out.data_ptr(), b * l, l, d)
     return out
 
 
 def mha_small(qkv: torch.Tensor, b: int, l: int, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv fp16 [B*L, 3*D] (q | k | v) -> fp16 [B*L, D]; softmax scale = head_dim^-0.5"""
-    L = _lib.load()
     d = qkv.shape[1] // 3
     dh = d // heads
     if out is None:
         out = torch.empty((b * l, d), device=qkv.device, dtype=torch.float16)
-    _lib.check(L.udt_mha_small(qkv.data_ptr(), out.data_ptr(), b, l, heads, dh, qkv.stride(0), out.stride(0),
-                               float(dh) ** -0.5, _stream()), "udt_mha_small")
+    _invoke("udt_mha_small", qkv.data_ptr(), out.data_ptr(), b, l, heads, dh, qkv.stride(0), out.stride(0),
+                               float(dh) ** -0.5)
     return out
 
 
 def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
-    L = _lib.load()
     rows, cols = x.shape
-    _lib.check(L.udt_softmax_rows(x.data_ptr(), rows, cols, x.stride(0), float(scale), _stream()), "udt_softmax_rows")
+    _invoke("udt_softmax_rows", x.data_ptr(), rows, cols, x.stride(0), float(scale))
     return x
 
 
 def cfg_pack(x: torch.Tensor, cat_uc: torch.Tensor, cat_c: torch.Tensor, c_in_dev: torch.Tensor, out: torch.Tensor
              ) -> torch.Tensor:
     """x fp32 NCHW [B,4,h,w], cat_* fp32 NCHW [B,5,h,w], c_in_dev: device fp32 scalar -> out fp16 NHWC [2B,h,w,16]"""
-    L = _lib.load()
     b = x.shape[0]
     hw = x.numel() // (b * 4)
-    _lib.check(L.udt_cfg_pack(x.data_ptr(), cat_uc.data_ptr(), cat_c.data_ptr(), out.data_ptr(), b, hw,
-                              c_in_dev.data_ptr(), _stream()), "udt_cfg_pack")
+    _invoke("udt_cfg_pack", x.data_ptr(), cat_uc.data_ptr(), cat_c.data_ptr(), out.data_ptr(), b, hw,
+                              c_in_dev.data_ptr())
     return out
 
 
 def cfg_euler_step_(x: torch.Tensor, eps2b: torch.Tensor, cfg_scale: float, dsigma_dev: torch.Tensor) -> torch.Tensor:
     """x fp32 NCHW [B,4,h,w] += dsigma * cfg(eps2b fp32 NHWC [2B,h,w,4]); dsigma_dev: device fp32 scalar"""
-    L = _lib.load()
     b = x.shape[0]
     hw = x.numel() // (b * 4)
-    _lib.check(L.udt_cfg_euler_step(x.data_ptr(), eps2b.data_ptr(), b, hw, float(cfg_scale), dsigma_dev.data_ptr(),
-                                    _stream()), "udt_cfg_euler_step")
+    _invoke("udt_cfg_euler_step", x.data_ptr(), eps2b.data_ptr(), b, hw, float(cfg_scale), dsigma_dev.data_ptr())
     return x
 
 
 def vae_sample_pack(moments: torch.Tensor, noise_c: torch.Tensor, noise_uc: torch.Tensor, mask: torch.Tensor,
                     scale_factor: float) -> Tuple[torch.Tensor, torch.Tensor]:
     """moments fp32 NHWC [B,h,w,>=8]; noise fp32 NCHW [B,4,h,w]; mask fp32 [B,1,8h,8w] -> (concat_c, concat_uc) NCHW"""
-    L = _lib.load()
     b, h, w, ld = moments.shape
     cat_c = torch.empty((b, 5, h, w), device=moments.device, dtype=torch.float32)
     cat_uc = torch.empty_like(cat_c)
-    _lib.check(L.udt_vae_sample_pack(moments.data_ptr(), ld, noise_c.data_ptr(), noise_uc.data_ptr(), mask.data_ptr(),
-                                     cat_c.data_ptr(), cat_uc.data_ptr(), b, h, w, float(scale_factor), _stream()),
-               "udt_vae_sample_pack")
+    _invoke("udt_vae_sample_pack", moments.data_ptr(), ld, noise_c.data_ptr(), noise_uc.data_ptr(), mask.data_ptr(),
+                                     cat_c.data_ptr(), cat_uc.data_ptr(), b, h, w, float(scale_factor))
     return cat_c, cat_uc
 
 
 def pointwise_affine(x: torch.Tensor, wm: torch.Tensor, bias: Optional[torch.Tensor], cpad: int, in_scale: float
                      ) -> torch.Tensor:
     """x fp32 NCHW [B,Cin,h,w] -> fp16 NHWC [B,h,w,cpad] = wm @ (x * in_scale) + bias"""
-    L = _lib.load()
     b, cin, h, w = x.shape
     out = torch.empty((b, h, w, cpad), device=x.device, dtype=torch.float16)
-    _lib.check(L.udt_pointwise_affine(x.data_ptr(), wm.data_ptr(), _ptr(bias), out.data_ptr(), b, h * w, cin, wm.shape[0],
-                                      cpad, float(in_scale), _stream()), "udt_pointwise_affine")
+    _invoke("udt_pointwise_affine", x.data_ptr(), wm.data_ptr(), _ptr(bias), out.data_ptr(), b, h * w, cin, wm.shape[0],
+                                      cpad, float(in_scale))
     return out
 
 
 def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    L = _lib.load()
     nb, h, w, c = x.shape
     if out is None:
         out = torch.empty((nb, 2 * h, 2 * w, c), device=x.device, dtype=torch.float16)
-    _lib.check(L.udt_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), nb, h, w, c, _stream()), "udt_upsample2x_nhwc")
+    _invoke("udt_upsample2x_nhwc", x.data_ptr(), out.data_ptr(), nb, h, w, c)
     return out
 
 
 def im2col3x3(x: torch.Tensor, stride: int, pad_lo: int, ho: int, wo: int, kpad: int,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    L = _lib.load()
     nb, h, w, c = x.shape
     if out is None:
         out = torch.empty((nb * ho * wo, kpad), device=x.device, dtype=torch.float16)
-    _lib.check(L.udt_im2col3x3_nhwc(x.data_ptr(), out.data_ptr(), nb, h, w, c, x.stride(2), stride, pad_lo, ho, wo, kpad,
-                                    _stream()), "udt_im2col3x3_nhwc")
+    _invoke("udt_im2col3x3_nhwc", x.data_ptr(), out.data_ptr(), nb, h, w, c, x.stride(2), stride, pad_lo, ho, wo, kpad)
     return out
 
 
 def nchw_to_nhwc_f16(x: torch.Tensor, cpad: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    L = _lib.load()
     nb, c, h, w = x.shape
     cpad = c if cpad is None else cpad
     if out is None:
         out = torch.empty((nb, h, w, cpad), device=x.device, dtype=torch.float16)
-    _lib.check(L.udt_nchw_f32_to_nhwc_f16(x.data_ptr(), out.data_ptr(), nb, c, h * w, cpad, _stream()),
-               "udt_nchw_f32_to_nhwc_f16")
+    _invoke("udt_nchw_f32_to_nhwc_f16", x.data_ptr(), out.data_ptr(), nb, c, h * w, cpad)
     return out
 
 
 def nhwc_to_nchw_f32(x: torch.Tensor, c: int, scale: float = 1.0, shift: float = 0.0, clamp01: bool = False,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    L = _lib.load()
     nb, h, w, ld = x.shape
     if out is None:
         out = torch.empty((nb, c, h, w), device=x.device, dtype=torch.float32)
-    _lib.check(L.udt_nhwc_to_nchw_f32(x.data_ptr(), int(x.dtype == torch.float32), out.data_ptr(), nb, c, h * w, ld,
-                                      float(scale), float(shift), int(clamp01), _stream()), "udt_nhwc_to_nchw_f32")
+    _invoke("udt_nhwc_to_nchw_f32", x.data_ptr(), int(x.dtype == torch.float32), out.data_ptr(), nb, c, h * w, ld,
+                                      float(scale), float(shift), int(clamp01))
     return out
