@@ -39,6 +39,7 @@ def main():
     for _ in range(reps):
         ops.SHAPE_LOG = []
         ops._prof = []
+        torch.cuda._sleep(40_000_000)  # GPU busy while the host enqueues: events then time pure device execution
         r._body()
         torch.cuda.synchronize()
         for (name, e0, e1), shape in zip(ops._prof, ops.SHAPE_LOG):

@@ -28,7 +28,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // fp16 elements per K step = one 128B swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                        // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                     // TMEM column offset of the second accumulator
 constexpr int kSmemBudget = 227 * 1024;
@@ -39,7 +39,8 @@ constexpr int kChunkBytes = kBlockM * kChunkCols * 2;  // 8 KB
 constexpr int kBiasImgs = 4;                        // per-image bias rows staged per tile (tiles spanning more images
                                                     // read rowbias from global memory)
 constexpr int kBiasBytes = kBiasImgs * 256 * 4;     // 4 KB
-constexpr int kEpiBarrier = 1;                      // named barrier id of the 4 epilogue warps
+constexpr int kEpiBarrier = 1;                      // named barrier ids 1, 2: the two epilogue warpgroups
+constexpr int kMaxResBufs = 4;
 
 struct IGemmParams {
   CUtensorMap mapA[3];
@@ -60,6 +61,9 @@ struct IGemmParams {
   void* out;
   int32_t ldo, out_fp32, act;
   int32_t staged;        // 1: smem-staged epilogue with TMA store (fp16 out), 0: direct global stores
+  int32_t egroups;       // staged mode: 1 or 2 epilogue warpgroups share a tile's chunks (2 for short-K, epilogue-bound GEMMs)
+  int32_t out_bufs;      // staged mode: output chunk buffers per group (2 or 3)
+  int32_t res_bufs;      // staged mode: residual chunk buffers per group (prefetch distance; 0 without residual)
   CUtensorMap mapOut;    // staged mode: {32, bw, bh, bn} boxes of the output tensor, 64B swizzle
   CUtensorMap mapRes;    // staged mode with residual: same boxes of the residual tensor
 };
@@ -157,15 +161,14 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_full = tmem_empty + 2;           // [2 groups][kMaxResBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2 * kMaxResBufs);
 
-  // staged epilogue buffers sit between the control block and the operand ring
+  // staged epilogue buffers (per epilogue group: out chunks, residual chunks, bias rows) sit between the control
+  // block and the operand ring
   const bool has_res_stage = p.staged && p.residual != nullptr;
-  const int epi_bytes = p.staged ? (2 * kChunkBytes + (has_res_stage ? 2 * kChunkBytes : 0) + kBiasBytes) : 0;
-  uint8_t* sOut = base + kCtrlBytes;
-  uint8_t* sRes = sOut + 2 * kChunkBytes;
-  float* sBias = reinterpret_cast<float*>(sOut + 2 * kChunkBytes + (has_res_stage ? 2 * kChunkBytes : 0));
+  const int group_bytes = (p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes;
+  const int epi_bytes = p.staged ? p.egroups * group_bytes : 0;
 
   const int b_bytes = p.BN * kBlockK * 2;
   uint8_t* sA = base + kCtrlBytes + epi_bytes;
@@ -185,9 +188,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
-      mbar_init(&res_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);
     }
+    for (int s = 0; s < 2 * kMaxResBufs; ++s) mbar_init(&res_full[s], 1);
     if (p.staged) {
       tma_prefetch_desc(&p.mapOut);
       if (p.residual != nullptr) tma_prefetch_desc(&p.mapRes);
@@ -265,11 +268,14 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       }
     }
   } else if (p.staged) {
-    // ------------------------------------------------------------------ staged epilogue (warps 2..5)
+    // ------------------------------------------------------------------ staged epilogue (warps 2..9, two groups)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
     const int row = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;             // 0..127 within the epilogue group
-    const bool leader = (et == 0);               // issues the TMA stores / residual prefetches
+    const int eg = (warp - 2) >> 2;              // epilogue group 0 / 1
+    const int et = threadIdx.x - 64 - eg * 128;  // 0..127 within the group
+    const bool leader = (et == 0);               // issues the group's TMA stores / residual prefetches
+    const bool active = eg < p.egroups;          // with one group, warps 6..9 only keep the TMEM hand-shake going
+    const uint32_t bar_id = kEpiBarrier + eg;
     const bool geglu = (p.act == UDT_ACT_GEGLU);
     const int cols_per_tile = geglu ? p.BN / 2 : p.BN;     // logical output columns per tile
     const int nchunks = cols_per_tile / kChunkCols;
@@ -278,74 +284,94 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     const int img_in_tile = row / bwh;           // which of the tile's images this row belongs to
     const bool bias_staged_rb = (p.rowbias == nullptr) || (p.bn <= kBiasImgs);
     const uint32_t swz = static_cast<uint32_t>((row >> 1) & 3);
+    uint8_t* sOut = base + kCtrlBytes + (active ? eg : 0) * group_bytes;
+    uint8_t* sRes = sOut + p.out_bufs * kChunkBytes;
+    float* sBias = reinterpret_cast<float*>(sRes + p.res_bufs * kChunkBytes);
+    uint64_t* my_res_full = res_full + eg * kMaxResBufs;
     uint8_t* my_out_row0 = sOut + row * 64;
     const uint8_t* my_res_row0 = sRes + row * 64;
+    const int estep = p.egroups;                 // this group handles every estep-th chunk of the CTA's chunk stream
 
-    // residual prefetch cursor: runs two chunks ahead of the consumer, across tile boundaries
-    int pf_tile = blockIdx.x, pf_chunk = 0;
+    // residual prefetch cursor: runs res_bufs chunks of this group ahead of the consumer, across tile boundaries
+    int pf_tile = blockIdx.x, pf_chunk = 0, pf_seq = 0;   // pf_seq: position in the CTA-wide chunk stream
     uint32_t pf_count = 0;
     auto prefetch_residual = [&]() {
+      while (pf_tile < p.num_tiles && (pf_seq % estep) != eg) {   // skip the other group's chunks
+        ++pf_seq;
+        if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += gridDim.x; }
+      }
       if (pf_tile >= p.num_tiles) return;
       const TileCoord t = decode_tile(p, pf_tile);
       const int col = t.n_blk * cols_per_tile + pf_chunk * kChunkCols;
-      const int b = pf_count & 1;
-      mbar_expect_tx(&res_full[b], kChunkBytes);
-      tma_load_4d(&p.mapRes, &res_full[b], sRes + b * kChunkBytes, col, t.w0, t.h0, t.n0);
+      const int b = pf_count % p.res_bufs;
+      mbar_expect_tx(&my_res_full[b], kChunkBytes);
+      tma_load_4d(&p.mapRes, &my_res_full[b], sRes + b * kChunkBytes, col, t.w0, t.h0, t.n0);
       ++pf_count;
-      if (++pf_chunk == nchunks) {
-        pf_chunk = 0;
-        pf_tile += gridDim.x;
-      }
+      ++pf_seq;
+      if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += gridDim.x; }
     };
-    if (has_res_stage && leader) {
-      prefetch_residual();
-      prefetch_residual();
+    if (has_res_stage && leader && active) {
+      for (int i = 0; i < p.res_bufs; ++i) prefetch_residual();
     }
 
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t g = 0;  // global chunk counter of this CTA (buffer = g & 1)
+    uint32_t g = 0;    // chunks processed by THIS group so far (buffer indices derive from it)
+    int seq = 0;       // position in the CTA-wide chunk stream
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int col_tile = tc.n_blk * cols_per_tile;
-      // ---- stage bias (+ per-image bias) of this tile's columns: global loads fly while the MMAs finish
-      float bv[2][kBiasImgs];
-      const int nimg = (p.rowbias != nullptr && bias_staged_rb) ? min(p.bn, kBiasImgs) : 1;
+      // does this group own any chunk of this tile?  (uniform over the group)
+      int first_c = (eg - (seq % estep) + estep) % estep;
+      const bool has_work = active && first_c < nchunks;
+      int last_c = -1;
+      if (has_work) last_c = first_c + ((nchunks - 1 - first_c) / estep) * estep;
+      const float* my_bias = sBias;
+      if (has_work) {
+        // ---- stage bias (+ per-image bias) of this tile's columns: global loads fly while the MMAs finish
+        float bv[2][kBiasImgs];
+        const int nimg = (p.rowbias != nullptr && bias_staged_rb) ? min(p.bn, kBiasImgs) : 1;
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int cc = et + h2 * 128;              // column within the (packed) tile, < BN <= 256
-        const int gcol = tc.n_blk * p.BN + cc;
-        const bool ok = (cc < p.BN) && (gcol < p.N_out);
-        const float b0 = (ok && p.bias != nullptr) ? __ldg(p.bias + gcol) : 0.0f;
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int cc = et + h2 * 128;              // column within the (packed) tile, < BN <= 256
+          const int gcol = tc.n_blk * p.BN + cc;
+          const bool ok = (cc < p.BN) && (gcol < p.N_out);
+          const float b0 = (ok && p.bias != nullptr) ? __ldg(p.bias + gcol) : 0.0f;
 #pragma unroll
-        for (int im = 0; im < kBiasImgs; ++im) {
-          float v = b0;
-          if (ok && im < nimg && p.rowbias != nullptr && bias_staged_rb) {
-            const int img = min(tc.n0 + im, p.NB - 1);
-            v += __ldg(p.rowbias + static_cast<size_t>(img) * p.ld_rowbias + gcol);
+          for (int im = 0; im < kBiasImgs; ++im) {
+            float v = b0;
+            if (ok && im < nimg && p.rowbias != nullptr && bias_staged_rb) {
+              const int img = min(tc.n0 + im, p.NB - 1);
+              v += __ldg(p.rowbias + static_cast<size_t>(img) * p.ld_rowbias + gcol);
+            }
+            bv[h2][im] = v;
           }
-          bv[h2][im] = v;
         }
-      }
-      named_bar_sync(kEpiBarrier, 128);            // previous tile's readers of sBias are done
+        named_bar_sync(bar_id, 128);               // previous tile's readers of sBias are done
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int cc = et + h2 * 128;
-        if (cc < p.BN) {
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int cc = et + h2 * 128;
+          if (cc < p.BN) {
 #pragma unroll
-          for (int im = 0; im < kBiasImgs; ++im)
-            if (im < nimg) sBias[im * 256 + cc] = bv[h2][im];
+            for (int im = 0; im < kBiasImgs; ++im)
+              if (im < nimg) sBias[im * 256 + cc] = bv[h2][im];
+          }
         }
+        named_bar_sync(bar_id, 128);
+        my_bias = sBias + ((p.rowbias != nullptr && bias_staged_rb) ? min(img_in_tile, kBiasImgs - 1) * 256 : 0);
       }
-      named_bar_sync(kEpiBarrier, 128);
-      const float* my_bias = sBias + ((p.rowbias != nullptr && bias_staged_rb) ? min(img_in_tile, kBiasImgs - 1) * 256 : 0);
       const int my_img = min(tc.n0 + img_in_tile, p.NB - 1);
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
-      for (int c = 0; c < nchunks; ++c, ++g) {
-        const int b = g & 1;
+      if (!has_work) {                             // nothing to read: release our share of the accumulator buffer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      }
+      for (int c = first_c; has_work && c < nchunks; c += estep, ++g) {
+        const int b = g % p.out_bufs;
         const int c0 = c * kChunkCols;
         float f[32];
         if (geglu) {
@@ -385,14 +411,15 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
         }
-        if (c == nchunks - 1) {                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        if (c == last_c) {                         // our last read of this accumulator: hand our share back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
         if (has_res_stage) {
-          mbar_wait(&res_full[b], (g >> 1) & 1);
-          const uint8_t* rrow = my_res_row0 + b * kChunkBytes;
+          const int rb_i = g % p.res_bufs;
+          mbar_wait(&my_res_full[rb_i], (g / p.res_bufs) & 1);
+          const uint8_t* rrow = my_res_row0 + rb_i * kChunkBytes;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 rv = *reinterpret_cast<const uint4*>(rrow + ((static_cast<uint32_t>(q) ^ swz) << 4));
@@ -405,9 +432,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             }
           }
         }
-        // the TMA store that last used sOut[b] (two chunks ago) must have finished reading it
-        if (leader) tma_store_wait_read<1>();
-        named_bar_sync(kEpiBarrier, 128);
+        // the TMA store that last used sOut[b] (out_bufs chunks ago) must have finished reading it
+        if (leader) {
+          if (p.out_bufs == 3) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+        }
+        named_bar_sync(bar_id, 128);
         uint8_t* orow = my_out_row0 + b * kChunkBytes;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -419,20 +448,29 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(q) ^ swz) << 4)) = ov;
         }
         fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(kEpiBarrier, 128);          // chunk complete in sOut[b]; sRes[b] fully consumed
+        named_bar_sync(bar_id, 128);               // chunk complete in sOut[b]; the residual buffer is consumed
         if (leader) {
           const int col = col_tile + c0;
-          if (col < n_logical) {
-            tma_store_4d(&p.mapOut, sOut + b * kChunkBytes, col, tc.w0, tc.h0, tc.n0);
-          }
+          if (col < n_logical) tma_store_4d(&p.mapOut, sOut + b * kChunkBytes, col, tc.w0, tc.h0, tc.n0);
           tma_store_commit();
-          if (has_res_stage) prefetch_residual();  // refill sRes[b] with the chunk two ahead
+          if (has_res_stage) prefetch_residual();  // refill the residual buffer just consumed
         }
       }
+      seq += nchunks;
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
-    if (leader) tma_store_wait_all<0>();           // all output tiles written before the CTA retires
+    if (leader && active) tma_store_wait_all<0>();   // all output tiles written before the CTA retires
+  } else if (warp >= 6) {
+    // ------------------------------------------------------------------ direct mode: warps 6..9 only hand-shake
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_full[as], aphase);
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
   } else {
     // ------------------------------------------------------------------ direct epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
@@ -661,11 +699,25 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   if (p.staged) {
     rc = make_tmap_nhwc_c32(&p.mapOut, d->out, static_cast<uint64_t>(n_logical), W, H, NB, d->ldo, p.bw, p.bh, p.bn);
     if (rc != UDT_OK) return rc;
-    epi_bytes = 2 * kChunkBytes + kBiasBytes;
+    // short-K GEMMs are epilogue-bound: two epilogue warpgroups and deeper chunk buffering; long-K tiles hide a
+    // single group's epilogue behind the mainloop and keep the shared memory for operand stages instead
+    const bool short_k = (ktotal / 64) <= 24;
+    p.egroups = short_k ? 2 : 1;
+    p.out_bufs = short_k ? 3 : 2;
+    p.res_bufs = 0;
     if (d->residual != nullptr) {
       rc = make_tmap_nhwc_c32(&p.mapRes, d->residual, static_cast<uint64_t>(n_logical), W, H, NB, d->ldr, p.bw, p.bh, p.bn);
       if (rc != UDT_OK) return rc;
-      epi_bytes += 2 * kChunkBytes;
+      p.res_bufs = short_k ? 3 : 2;
+    }
+    epi_bytes = p.egroups * ((p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes);
+    const int stage_b = kABytes + BN * kBlockK * 2;
+    if (short_k && (kSmemBudget - kCtrlBytes - 1024 - epi_bytes) / stage_b < 3) {
+      // wide column tiles: keep at least 3 operand stages, fall back to the shallow single-group epilogue
+      p.egroups = 1;
+      p.out_bufs = 2;
+      p.res_bufs = d->residual != nullptr ? 2 : 0;
+      epi_bytes = (p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes;
     }
   }
   const int stage_bytes = kABytes + BN * kBlockK * 2;

@@ -60,6 +60,9 @@ def profile_step(runner, warm: int = 2, reps: int = 3) -> dict:
     for _ in range(reps):
         _prof = []
         try:
+            # keep the GPU busy while the host enqueues the whole step, so that the event pairs time back-to-back
+            # kernel execution instead of the host's launch cadence
+            torch.cuda._sleep(40_000_000)
             runner._body()
             torch.cuda.synchronize()
             for name, e0, e1 in _prof:
