@@ -167,24 +167,11 @@ def run_b200(args):
 
     # global synthetic request (seeded), this rank's rows; pinned host copies for the e2e leg
     full = synth.synthetic_batch(2, gb, IMG, IMG, LABEL_LEN)
-    lo, hi = rank * B, (rank + 1) * B
-
-    def shard_rows(pin: bool):
-        out = {}
-        for k, v in full.items():
-            if isinstance(v, torch.Tensor):
-                t = v[lo:hi].contiguous()
-                out[k] = t.pin_memory() if pin else t
-            elif isinstance(v, list):
-                out[k] = v[lo:hi]
-            else:
-                out[k] = v
-        return out
-
-    host_batch = shard_rows(pin=True)
+    lo, hi = api.shard_bounds(gb, rank, world)
+    host_batch = {k: (v.contiguous().pin_memory() if isinstance(v, torch.Tensor) else v)
+                  for k, v in api.shard_batch(full, lo, hi).items()}
     dev_batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
     h2d = sum(v.numel() * v.element_size() for v in host_batch.values() if isinstance(v, torch.Tensor))
-    gathered = torch.empty((gb, 3, IMG, IMG), device=dev, dtype=torch.float32) if world > 1 else None
     host_out = torch.empty((gb if world > 1 else B, 3, IMG, IMG), dtype=torch.float32).pin_memory()
     d2h = host_out.numel() * 4
 
@@ -192,8 +179,7 @@ def run_b200(args):
         torch.manual_seed(seed)
         img, _ = api.predict(cfgs, model, sampler, dict(batch), shard=(gb, lo, hi))
         if world > 1:
-            dist.all_gather_into_tensor(gathered, img.contiguous())   # the path's one collective
-            img = gathered
+            img = api.all_gather_images(img, gb)   # the path's one collective: ncclAllGather of decoded images
         if to_host:
             host_out.copy_(img, non_blocking=True)
         return img
@@ -230,7 +216,7 @@ def run_b200(args):
 
     runner = sampler.last_runner
     # kernels launched in the timed region: graph replays (captured launches per step) + eager conditioner/decoder calls
-    launches = eager_calls + args.steps * DDIM_STEPS * max(runner.launches_per_step, 1) - args.steps * DDIM_STEPS * 0
+    launches = eager_calls + args.steps * DDIM_STEPS * max(runner.launches_per_step, 1)
     # ---- per-kernel-class timing of ONE UNet CFG step, live, CUDA events on the launching stream (eager replay)
     prof = ops.profile_step(runner, warm=2, reps=3)
     peaks = measured_peaks()

@@ -36,6 +36,7 @@ int udt_version(void);            /* ABI version (2) */
 int udt_arch(void);               /* compute capability of the current device *10 (100 on B200); <0 on error */
 const char* udt_last_error(void); /* thread-local message of the last failing call */
 int udt_num_sms(void);
+int udt_sizeof_igemm_desc(void);  /* sizeof(udt_igemm_desc) as compiled: lets a foreign-language binding check its struct mirror */
 
 /* One K-segment of the implicit GEMM: an NHWC fp16 activation tensor read either point-wise (taps = 1:
  * nn.Linear / 1x1 conv) or through a 3x3 window (taps = 9) with zero padding, stride 1 or 2. */

@@ -1,0 +1,66 @@
+"""C-ABI checks that need no GPU: the library builds for sm_100a, loads, exports every symbol include/udt_api.h
+declares, its descriptor struct matches the ctypes mirror, and compute entry points FAIL LOUDLY (no CPU fallback)
+when no sm_100 device is present."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "udt_api.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(udt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(udt_lib):
+    from udifftext_b200 import lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(udt_lib, name), f"{name} declared in include/udt_api.h but not exported by libudt_b200.so"
+    assert set(declared) == set(lib.EXPORTED_SYMBOLS), set(declared) ^ set(lib.EXPORTED_SYMBOLS)
+
+
+def test_descriptor_layout_and_constants(udt_lib):
+    from udifftext_b200 import lib, pack
+    assert udt_lib.udt_version() == 2
+    assert udt_lib.udt_sizeof_igemm_desc() == ctypes.sizeof(lib.IGemmDesc)
+    assert udt_lib.udt_geglu_tile() == pack.GEGLU_TILE
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_calls_fail_loudly_without_sm100(udt_lib):
+    from udifftext_b200 import lib
+    rc = udt_lib.udt_layernorm(None, None, 1, 8, None, None, 1e-5, None)
+    assert rc == -3  # UDT_ERR_ARCH
+    assert b"no CPU path" in udt_lib.udt_last_error() or b"sm_" in udt_lib.udt_last_error()
+    with pytest.raises(lib.UdtError):
+        lib.check(rc, "udt_layernorm")
+    d = lib.IGemmDesc()
+    assert udt_lib.udt_igemm(ctypes.byref(d), None) == -3
+
+
+def test_host_objects_refuse_cpu_devices():
+    from udifftext_b200 import api
+    eng = api.build_engine("tiny")
+    with pytest.raises(RuntimeError):
+        eng.to("cpu")
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions(udt_lib):
+    """the built library carries tcgen05 (UTC*MMA), TMEM loads (LDTM) and TMA (UTMALDG/UTMASTG) SASS"""
+    import shutil
+    import subprocess
+    from udifftext_b200 import lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "STTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")  # no legacy mma.sync path

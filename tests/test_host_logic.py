@@ -1,0 +1,220 @@
+"""Host-side logic that needs no GPU: schedule / denoiser constants, config injection, state_dict layout, weight
+packing, label indexing, RNG sharding, the drop-in `sgm` package and (in the build container, where the reference is
+mounted) agreement of the host classes with the unmodified reference's."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("UDT_REFERENCE_ROOT", "/root/reference")
+has_ref = os.path.isdir(os.path.join(REF, "sgm"))
+
+
+def test_schedule_matches_oracle():
+    from oracle import restated as R
+    from udifftext_b200.host import schedule as S
+    disc = S.LegacyDDPMDiscretization()
+    for n in (2, 10, 50, 100, 1000):
+        assert torch.equal(disc(n), R.sampler_sigmas(n))
+    den = S.DiscreteDenoiser({"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+                             {"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}, 1000,
+                             {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    assert torch.equal(den.sigmas, R.denoiser_sigmas())
+    k = S.step_constants(den, disc(50))
+    assert k["idx"].tolist() == list(range(999, 0, -20))         # integer timesteps 999, 979, ..., 19
+    assert torch.equal(k["eps_scale"], torch.ones(50))            # sampler sigmas lie on the denoiser table
+    sig = disc(50)
+    assert torch.allclose(k["c_in"], 1 / (sig[:-1] ** 2 + 1) ** 0.5)
+    assert torch.equal(k["dsigma"], sig[1:] - sig[:-1])
+    with pytest.raises(ValueError):
+        disc(1001)
+
+
+def test_denoiser_and_guider_generic_formulation():
+    """Denoiser.__call__ / VanillaCFG on a stand-in network: same algebra as oracle.cfg_denoise_eps"""
+    from udifftext_b200.host import schedule as S
+    den = S.DiscreteDenoiser({"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+                             {"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}, 1000,
+                             {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 4, 8, 8), generator=g)
+    seen = {}
+
+    def net(xin, t, cond):
+        seen["t"], seen["cat"] = t, cond["concat"]
+        return 0.5 * xin
+
+    guider = S.VanillaCFG(scale=5.0)
+    c = {"concat": torch.ones((2, 5, 8, 8)), "t_crossattn": torch.ones((2, 12, 16))}
+    uc = {"concat": torch.zeros((2, 5, 8, 8)), "t_crossattn": torch.zeros((2, 12, 16))}
+    sigma = torch.full((2,), float(den.sigmas[979]))
+    xin, s2, cc = guider.prepare_inputs(x, sigma, c, uc)
+    assert xin.shape[0] == 4 and torch.equal(cc["concat"][:2], uc["concat"]) and torch.equal(cc["concat"][2:], c["concat"])
+    out = guider(den(net, xin, s2, cc), s2)
+    assert seen["t"].tolist() == [979] * 4 and seen["t"].dtype == torch.int64
+    c_in = 1 / (sigma[0] ** 2 + 1) ** 0.5
+    expect = x + (-sigma[0]) * 0.5 * c_in * x   # uncond == cond here, so CFG is the identity
+    assert torch.allclose(out, expect, atol=1e-6)
+
+
+def test_config_injection_and_state_dict_layout():
+    from udifftext_b200 import api, synth
+    from udifftext_b200.host.config import instantiate_from_config
+    eng = instantiate_from_config(api.model_config("tiny"))
+    assert type(eng).__name__ == "DiffusionEngine" and type(eng.model).__name__ == "OpenAIWrapper"
+    assert [type(e).__name__ for e in eng.conditioner.embedders] == ["LabelEncoder", "SpatialRescaler", "LatentEncoder"]
+    sd = synth.synthetic_state_dict(synth.load_manifest("tiny"), 1234)
+    assert eng.load_state_dict(sd, strict=True) == ([], [])
+    back = eng.state_dict()
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    with pytest.raises(RuntimeError):
+        eng.load_state_dict({"bogus.weight": torch.zeros(1)}, strict=True)
+    with pytest.raises(NotImplementedError):
+        instantiate_from_config({"target": "sgm.modules.encoders.modules.FrozenCLIPEmbedder"})
+    with pytest.raises(NotImplementedError):
+        eng.train()
+    # full-size manifest has the reference's 1330 tensors and the documented key families
+    full = synth.load_manifest("full")
+    assert len(full) == 1330 and full["denoiser.sigmas"] == [1000] and full["loss_fn.g_kernel"] == [12, 1, 3, 3]
+
+
+def test_label_indices_and_charset():
+    from oracle import restated as R
+    from udifftext_b200 import label
+    labs = ["Ab9!", "", "x" * 12, "~\t"]
+    assert torch.equal(label.label_indices(labs, 12).long(), R.label_indices(labs, 12))
+    assert label.label_indices(["a"], 12)[0, 0].item() == label.CHARSET.find("a") + 1
+    with pytest.raises(AssertionError):
+        label.label_indices(["x" * 13], 12)
+
+
+def _emulate_igemm(x_nhwc, wp, taps_c):
+    """reference semantics of the packed weight layout: K ordered (tap, channel padded to 64)"""
+    nb, h, w, c = x_nhwc.shape
+    c64 = (c + 63) // 64 * 64
+    xp = F.pad(x_nhwc, (0, c64 - c, 1, 1, 1, 1))
+    cols = [xp[:, ky: ky + h, kx: kx + w, :] for ky in range(3) for kx in range(3)]
+    a = torch.cat(cols, dim=-1).reshape(nb * h * w, 9 * c64)
+    return (a @ wp[:, : 9 * c64].float().t()).reshape(nb, h, w, -1)
+
+
+@pytest.mark.parametrize("cin,cstore", [(9, 16), (64, 64), (96, 96), (3, 8)])
+def test_pack_conv3x3_layout(cin, cstore):
+    from udifftext_b200 import pack
+    g = torch.Generator().manual_seed(cin)
+    x = torch.randn((2, cin, 6, 5), generator=g).half().float()
+    wt = (torch.randn((8, cin, 3, 3), generator=g) / math.sqrt(9 * cin)).half().float()
+    ref = F.conv2d(x, wt, padding=1).permute(0, 2, 3, 1)
+    xh = torch.zeros((2, 6, 5, cstore))
+    xh[..., :cin] = x.permute(0, 2, 3, 1)
+    wp = pack.pack_conv3x3(wt, cin_pad=cstore)
+    assert wp.shape[1] % 64 == 0 and wp.dtype == torch.float16
+    assert torch.allclose(_emulate_igemm(xh, wp, cin), ref, atol=1e-4)
+
+
+def test_pack_geglu_interleave():
+    from udifftext_b200 import pack
+    g = torch.Generator().manual_seed(1)
+    c = 64
+    w, b = torch.randn((8 * c, c), generator=g), torch.randn((8 * c,), generator=g)
+    wp, bp = pack.pack_geglu(w, b)
+    t = pack.GEGLU_TILE
+    # tile 1: x rows [t/2, t) then gate rows [4c + t/2, 4c + t)
+    assert torch.equal(wp[t: t + t // 2].float(), w[t // 2: t].half().float())
+    assert torch.equal(wp[t + t // 2: 2 * t].float(), w[4 * c + t // 2: 4 * c + t].half().float())
+    assert torch.equal(bp[t + t // 2: 2 * t], b[4 * c + t // 2: 4 * c + t])
+
+
+def test_rng_shard_slices_the_global_draw():
+    from udifftext_b200.host import rng
+    torch.manual_seed(3)
+    full = torch.randn((6, 4, 2, 2))
+    torch.manual_seed(3)
+    with rng.batch_shard(6, 2, 5):
+        part = rng.randn((3, 4, 2, 2), "cpu")
+    assert torch.equal(part, full[2:5])
+    torch.manual_seed(3)
+    assert torch.equal(rng.randn((6, 4, 2, 2), "cpu"), full)
+
+
+def test_shard_bounds_cover_the_batch():
+    from udifftext_b200 import api
+    for gb in (1, 4, 7, 64):
+        for world in (1, 2, 3, 8):
+            spans = [api.shard_bounds(gb, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == gb
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_min_local_loss_matches_formula():
+    """FullLoss.get_min_local_loss against a direct evaluation of loss.py:192-235's formula, incl. batch > 1"""
+    from udifftext_b200.host.loss import FullLoss
+    g = torch.Generator().manual_seed(5)
+    loss = FullLoss(seq_len=12, kernel_size=3, gaussian_sigma=1.0, min_attn_size=4)
+    assert abs(loss.g_kernel.sum().item() - 12.0) < 1e-5 and tuple(loss.g_kernel.shape) == (12, 1, 3, 3)
+    b, heads, size = 2, 2, 4
+    probs = torch.rand((2 * b * heads, size * size, 12), generator=g).softmax(-1)
+    cache = [{"name": "blk.t_attn", "heads": heads, "size": size, "attn_map": probs},
+             {"name": "blk.small.t_attn", "heads": heads, "size": 2, "attn_map": torch.rand((2 * b * heads, 4, 12), generator=g)}]
+    mask = (torch.rand((b, 1, 32, 32), generator=g) > 0.5).float()
+    seg = torch.zeros((b, 12)); seg[0, :3] = 1; seg[1, :7] = 1
+    got = loss.get_min_local_loss(cache, mask, seg)
+    assert got.shape == (2 * b,)
+    am = probs.reshape(2 * b, heads, size * size, 12).mean(1).permute(0, 2, 1).reshape(2 * b, 12, size, size)
+    am = F.conv2d(am, loss.g_kernel, padding=1, groups=12).reshape(2 * b, 12, -1)
+    mm = F.interpolate(mask, (size, size)).reshape(b, 1, -1).repeat(2, 12, 1)
+    expect = -((mm * am).max(-1)[0] + (1 - seg.repeat(2, 1))).min(-1)[0]
+    assert torch.allclose(got, expect, atol=1e-6)
+
+
+def test_dropin_sgm_package_resolves_reference_paths():
+    import importlib
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "import sgm; from sgm.util import instantiate_from_config;"
+            "from sgm.modules.diffusionmodules.sampling import *;"
+            "import sgm.models.diffusion as d, sgm.modules.encoders.modules as m, sgm.modules.diffusionmodules.openaimodel as o;"
+            "assert sgm.__file__.startswith(%r);"
+            "print(EulerEDMSampler.__module__, d.DiffusionEngine.__name__, m.LabelEncoder.__name__, o.UnifiedUNetModel.__name__)"
+            % (ROOT, os.path.join(ROOT, "udifftext_b200", "dropin"), ROOT))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "udifftext_b200.host.sampler DiffusionEngine LabelEncoder UnifiedUNetModel" in out.stdout
+
+
+@pytest.mark.skipif(not has_ref, reason="reference checkout not mounted (GPU box)")
+def test_reference_util_py_runs_unchanged_on_the_dropin():
+    """the reference's own util.py (unmodified, executed from /root/reference) builds OUR sampler through the
+    drop-in sgm package; omegaconf (not installed here) is stubbed because util.py imports it at module scope"""
+    import subprocess
+    code = ("import sys, types, runpy; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "oc = types.ModuleType('omegaconf'); oc.OmegaConf = type('OmegaConf', (), {}); sys.modules['omegaconf'] = oc;"
+            "ns = runpy.run_path(%r);"
+            "from udifftext_b200 import api; cfgs = api.runtime_config(steps=7, gpu=0);"
+            "s = ns['init_sampling'](cfgs);"
+            "print(type(s).__module__, type(s).__name__, s.num_steps, type(s.guider).__name__, s.guider.scale, len(s.discretization(7)))"
+            % (ROOT, os.path.join(ROOT, "udifftext_b200", "dropin"), os.path.join(REF, "util.py")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "udifftext_b200.host.sampler EulerEDMSampler 7 VanillaCFG 5.0 8" in out.stdout
+
+
+@pytest.mark.skipif(not has_ref, reason="reference checkout not mounted (GPU box)")
+def test_host_schedule_equals_unmodified_reference_classes():
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r);"
+            "from oracle import ref_import; ref_import.import_reference();"
+            "import torch;"
+            "from sgm.modules.diffusionmodules.discretizer import LegacyDDPMDiscretization as RefD;"
+            "from udifftext_b200.host.schedule import LegacyDDPMDiscretization as OurD;"
+            "assert all(torch.equal(RefD()(n), OurD()(n)) for n in (2, 10, 50, 1000));"
+            "assert torch.equal(RefD()(1000, do_append_zero=False, flip=True), OurD()(1000, do_append_zero=False, flip=True));"
+            "print('equal')" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "equal" in out.stdout

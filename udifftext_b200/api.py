@@ -138,3 +138,44 @@ def predict(cfgs, model, sampler, batch: Dict, shard: Optional[Tuple[int, int, i
                             detailed=cfgs.detailed)
         samples = model.decode_first_stage_clamped(samples_z)
     return samples, samples_z
+
+
+# ------------------------------------------------------------------------------------------------- multi-GPU
+def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """rows [lo, hi) of a request batch owned by `rank`: contiguous, sizes differ by at most one"""
+    base, rem = divmod(int(global_batch), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: Dict, lo: int, hi: int) -> Dict:
+    """rows [lo, hi) of every per-sample entry of a request batch (tensors and lists)"""
+    n = len(batch["label"]) if "label" in batch else None
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, torch.Tensor) and (n is None or v.shape[0] == n):
+            out[k] = v[lo:hi]
+        elif isinstance(v, list) and (n is None or len(v) == n):
+            out[k] = v[lo:hi]
+        else:
+            out[k] = v
+    return out
+
+
+def all_gather_images(samples: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
+    """The path's only collective: every rank contributes its decoded images [hi-lo, 3, H, W] and receives the whole
+    request [global_batch, 3, H, W] in request order (ncclAllGather over NVLink; gloo in the CPU tests).  Equal
+    shards use one all_gather_into_tensor; ragged shards are padded to the largest shard."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
+    big = max(hi - lo for lo, hi in sizes)
+    mine = samples.contiguous()
+    if mine.shape[0] < big:
+        mine = torch.cat([mine, mine.new_zeros((big - mine.shape[0],) + tuple(mine.shape[1:]))])
+    out = mine.new_empty((world * big,) + tuple(mine.shape[1:]))
+    dist.all_gather_into_tensor(out, mine, group=group)
+    if all(hi - lo == big for lo, hi in sizes):
+        return out
+    return torch.cat([out[r * big: r * big + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])

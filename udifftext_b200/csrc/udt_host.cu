@@ -141,4 +141,5 @@ int udt_version(void) { return 2; }
 int udt_arch(void) { return udt_host::arch(); }
 const char* udt_last_error(void) { return udt_host::error_buffer(); }
 int udt_num_sms(void) { return udt_host::num_sms(); }
+int udt_sizeof_igemm_desc(void) { return static_cast<int>(sizeof(udt_igemm_desc)); }
 }

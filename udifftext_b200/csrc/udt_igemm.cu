@@ -19,6 +19,7 @@
 // Replaces the cuDNN / cuBLAS call sites listed in include/udt_api.h (udt_igemm).
 #include "udt_common.cuh"
 #include "udt_host.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -60,6 +61,7 @@ struct IGemmParams {
   int32_t ldr, ld_rowbias;
   void* out;
   int32_t ldo, out_fp32, act;
+  int32_t debug;         // UDT_IGEMM_DEBUG experiment flags (0 in production)
   int32_t staged;        // 1: smem-staged epilogue with TMA store (fp16 out), 0: direct global stores
   int32_t egroups;       // staged mode: 1 or 2 epilogue warpgroups share a tile's chunks (2 for short-K, epilogue-bound GEMMs)
   int32_t out_bufs;      // staged mode: output chunk buffers per group (2 or 3)
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
         named_bar_sync(bar_id, 128);               // chunk complete in sOut[b]; the residual buffer is consumed
         if (leader) {
           const int col = col_tile + c0;
-          if (col < n_logical) tma_store_4d(&p.mapOut, sOut + b * kChunkBytes, col, tc.w0, tc.h0, tc.n0);
+          if (col < n_logical && !(p.debug & 1)) tma_store_4d(&p.mapOut, sOut + b * kChunkBytes, col, tc.w0, tc.h0, tc.n0);
           tma_store_commit();
           if (has_res_stage) prefetch_residual();  // refill the residual buffer just consumed
         }
@@ -735,6 +737,16 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   p.out_fp32 = d->out_fp32;
   p.act = act;
 
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("UDT_IGEMM_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  p.debug = dbg;
+  if (dbg & 0xF00) {
+    const int force = (dbg >> 8) & 0xF;
+    if (force >= 2 && force <= stages) stages = force, p.stages = force;
+  }
   const int smem = kCtrlBytes + 1024 + epi_bytes + stages * stage_bytes;
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   udt_igemm_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "udt_arch": (c_int32, []),
     "udt_last_error": (c_char_p, []),
     "udt_num_sms": (c_int32, []),
+    "udt_sizeof_igemm_desc": (c_int32, []),
     "udt_geglu_tile": (c_int32, []),
     "udt_igemm": (c_int32, [POINTER(IGemmDesc), c_void_p]),
     "udt_groupnorm_ws_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
