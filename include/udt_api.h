@@ -82,6 +82,10 @@ typedef struct {
 int udt_igemm(const udt_igemm_desc* desc, void* stream);
 /* column tile (BN) the GEGLU weight interleave must be packed for (x half then gate half per tile) */
 int udt_geglu_tile(void);
+/* tuning aid (scripts/igemm_trace.py): while `buf` (device memory, nbytes) is set, every udt_igemm launch whose
+ * grid fits writes per-CTA role timestamps into it; buf = NULL switches tracing off.  Returns the number of
+ * 8-byte slots per CTA. */
+int udt_debug_set_trace(void* buf, int64_t nbytes);
 
 /* K1 — GroupNorm(32 groups)(+SiLU) over NHWC fp16, fp32 statistics; optionally normalises the channel
  * concatenation of two tensors (`x1` may be NULL) and writes one [NB, HW, C0+C1] tensor.

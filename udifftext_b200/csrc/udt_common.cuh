@@ -74,6 +74,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters (CTA pairs for tcgen05 cta_group::2, DSMEM exchange) and programmatic dependent launch
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ double ld_shared_cluster_f64(uint32_t cluster_addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+// Programmatic dependent launch: `griddep_wait` blocks until the kernels this launch depends on have completed and
+// their memory is visible (no-op without the launch attribute); `griddep_launch` lets the dependent grid start its
+// prologue early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -98,6 +134,25 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// CTA-pair variants (tcgen05 cta_group::2): the data lands in the executing CTA's shared memory, the transaction
+// bytes are signalled on the mbarrier at `bar_cluster_addr` (a shared::cluster address, normally in the leader CTA)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                 int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -139,6 +194,18 @@ template <uint32_t kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
+// cta_group::2: one warp of EACH CTA of the pair executes these with the same shared-memory offset / column count
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -155,6 +222,27 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// CTA-pair MMA (M = 256 over two SMs): issued by one thread of the leader CTA; A/B descriptors address the same
+// shared-memory offsets in both CTAs (each CTA holds its 128 rows of A and its half of B's N rows).
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of cta_group::2 MMAs: arrives on the mbarrier at this shared-memory offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
       : "memory");
 }
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.

@@ -2,6 +2,7 @@
 #include "udt_host.h"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace udt_host {
@@ -68,6 +69,18 @@ int arch() {
   int rc = query_device(&dev);
   if (rc != UDT_OK) return rc;
   return g_arch[dev];
+}
+
+int pdl_attr(cudaLaunchAttribute* attr) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("UDT_PDL");
+    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled) return 0;
+  attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -17,6 +17,9 @@ int check_launch(const char* what);   // cudaGetLastError -> UDT_ERR_LAUNCH
 int require_sm100();                  // UDT_OK or UDT_ERR_ARCH (cached per device)
 int num_sms();
 int arch();                           // compute capability * 10 of the current device, or <0
+// Programmatic dependent launch (every kernel of this library executes griddepcontrol.wait before it touches
+// global memory): fills one launch attribute and returns 1, or returns 0 when disabled (UDT_PDL=0).
+int pdl_attr(cudaLaunchAttribute* attr);
 
 // 2-D fp16 tensor map, dim0 = contiguous (cols), box = {box0, box1}, 128B swizzle.
 int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box0,

@@ -2,10 +2,18 @@
 //
 //   out[m, n] = act( sum_{seg,tap,c} A_seg[pixel(m) + tap, c] * Wt[n, k] + bias[n] + rowbias[img(m), n] ) + res[m, n]
 //
+// Two launch shapes of the same kernel:
+//   pair   : clusters of two CTAs (one per SM of a TPC) drive tcgen05 cta_group::2 — one M = 256 tile per pair, each
+//            CTA loads its own 128 rows of A and HALF of the weight tile, which halves the per-SM operand traffic
+//            (the per-SM TMA ingest rate, ~73 B/clk measured, is what bounds these GEMMs); the leader CTA's MMA
+//            thread issues for both SMs, commits are multicast to both CTAs' barriers.
+//   single : one CTA per tile (tiny problems, fp32 / narrow outputs).
 // One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer   : per K step one 4-D box load {64 ch, bw, bh, bn} of the NHWC activation
-//                                (shifted by the 3x3 tap, out-of-bounds zero filled = conv padding) and one
-//                                2-D box load {64, BN} of the K-major fp16 weights, both 128B-swizzled.
+//   warp 0      A producer     : per K step one 4-D TMA box {64 ch, bw, bh, bn} of the NHWC activation (shifted by the
+//                                3x3 tap, out-of-bounds zero filled = conv padding), 128B-swizzled.
+//   warp 10     B producer     : per K step one 2-D TMA box {64, BN} of the K-major fp16 weights.  Two issuing threads
+//                                because ONE thread sustains only one TMA instruction per ~250 clk (measured) — with a
+//                                single producer every K step cost ~520 clk regardless of its size.
 //   warp 1      MMA issuer     : tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16, fp32 accumulators
 //                                in TMEM, two accumulator buffers so the epilogue of tile i overlaps tile i+1.
 //   warps 2..5  epilogue       : tcgen05.ld (thread = output row), bias / per-image bias / SiLU / ReLU / GEGLU /
@@ -29,12 +37,12 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // fp16 elements per K step = one 128B swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 320;                        // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kThreads = 352;                        // A-TMA warp, MMA warp, 2 x 4 epilogue warps, B-TMA warp
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                     // TMEM column offset of the second accumulator
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kCtrlBytes = 1024;
-constexpr int kGegluTile = 128;
+constexpr int kGegluTile = 256;                      // preferred GEGLU weight interleave (128 is accepted via bn_hint)
 constexpr int kChunkCols = 32;                      // epilogue staging granularity: 32 fp16 columns = 64 B rows
 constexpr int kChunkBytes = kBlockM * kChunkCols * 2;  // 8 KB
 constexpr int kBiasImgs = 4;                        // per-image bias rows staged per tile (tiles spanning more images
@@ -68,16 +76,38 @@ struct IGemmParams {
   int32_t res_bufs;      // staged mode: residual chunk buffers per group (prefetch distance; 0 without residual)
   CUtensorMap mapOut;    // staged mode: {32, bw, bh, bn} boxes of the output tensor, 64B swizzle
   CUtensorMap mapRes;    // staged mode with residual: same boxes of the residual tensor
+  unsigned long long* trace;  // udt_debug_set_trace(): per-CTA role timestamps (NULL in production)
 };
+
+// trace layout per CTA: [0] globaltimer at start, [1] at end, [2] clock64 at start, [3] at end, then per tile
+// iteration kTraceEvents clock64 stamps (see scripts/igemm_trace.py)
+constexpr int kTraceTiles = 24;
+constexpr int kTraceEvents = 8;
+constexpr int kTraceStride = 4 + kTraceTiles * kTraceEvents;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_ev(const IGemmParams& p, int iter, int ev) {
+  if (p.trace != nullptr && iter < kTraceTiles)
+    p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 4 + iter * kTraceEvents + ev] =
+        static_cast<unsigned long long>(clock64());
+}
 
 struct TileCoord {
   int w0, h0, n0, n_blk;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int tile) {
+// `tile` counts (M tile or M-tile pair, N tile); `rank` = CTA rank within the pair (0 in single mode).  An odd tile
+// count leaves a phantom M tile whose image coordinate is out of range: TMA zero-fills its loads and clips its stores.
+template <bool kPair>
+__device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int tile, int rank) {
   TileCoord t;
   t.n_blk = tile % p.tiles_n;
   int m_blk = tile / p.tiles_n;
+  if (kPair) m_blk = 2 * m_blk + rank;
   int tw = m_blk % p.tiles_w;
   int r = m_blk / p.tiles_w;
   int th = r % p.tiles_h;
@@ -153,7 +183,9 @@ __device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[
   for (int j = 0; j < cnt; ++j) o[j] = __float2half_rn(f[j]);
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_constant__ IGemmParams p) {
+  griddep_launch();   // PDL: the next kernel of the stream may start its prologue while this one runs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -172,7 +204,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
   const int group_bytes = (p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes;
   const int epi_bytes = p.staged ? p.egroups * group_bytes : 0;
 
-  const int b_bytes = p.BN * kBlockK * 2;
+  const int b_rows = kPair ? p.BN / 2 : p.BN;          // weight rows this CTA stages per K step
+  const int b_bytes = b_rows * kBlockK * 2;
+  const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   uint8_t* sA = base + kCtrlBytes + epi_bytes;
   uint8_t* sB = sA + p.stages * kABytes;
   const uint32_t sA_addr = base_addr + kCtrlBytes + epi_bytes;
@@ -185,12 +221,12 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.mapA[s]);
     tma_prefetch_desc(&p.mapB);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);    // the A and the B producer each arrive once (expect_tx) per K step
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], kPair ? 16 : 8);   // 8 epilogue warps per CTA; the leader's copy collects both CTAs
     }
     for (int s = 0; s < 2 * kMaxResBufs; ++s) mbar_init(&res_full[s], 1);
     if (p.staged) {
@@ -199,20 +235,31 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair<kTmemCols>(tmem_slot); else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // peer barriers must be initialised before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();     // PDL: everything above overlapped the previous kernel; its results are needed from here on
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 0] = globaltimer_ns();
+    p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 2] = static_cast<unsigned long long>(clock64());
+  }
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ A (activation) producer
+    // whole warp runs the warp-uniform loop (coordinates stay in uniform registers), one elected lane issues
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        int kstep = 0;
+      int iter = 0;
+      const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;   // the leader's full barriers
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
+        const TileCoord tc = decode_tile<kPair>(p, tile, rank);
+        if (issuer) trace_ev(p, iter, 0);
         for (int s = 0; s < p.nseg; ++s) {
           const CUtensorMap* ma = &p.mapA[s];
           const int taps = p.seg_taps[s];
@@ -221,11 +268,20 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           for (int t = 0; t < taps; ++t) {
             const int dy = (taps == 9) ? (t / 3 - p.seg_pad[s]) : 0;
             const int dx = (taps == 9) ? (t % 3 - p.seg_pad[s]) : 0;
-            for (int c = 0; c < kc; ++c, ++kstep) {
+            for (int c = 0; c < kc; ++c) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(kABytes + b_bytes));
-              tma_load_4d(ma, &full_bar[stage], sA + stage * kABytes, c * kBlockK, sw0 + dx, sh0 + dy, tc.n0);
-              tma_load_2d(&p.mapB, &full_bar[stage], sB + stage * b_bytes, kstep * kBlockK, tc.n_blk * p.BN);
+              if (issuer) {
+                if (kPair) {
+                  // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the whole pair
+                  if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(kABytes));
+                  tma_load_4d_pair(ma, full0 + static_cast<uint32_t>(stage) * 8u, sA + stage * kABytes, c * kBlockK,
+                                   sw0 + dx, sh0 + dy, tc.n0);
+                } else {
+                  mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(kABytes));
+                  tma_load_4d(ma, &full_bar[stage], sA + stage * kABytes, c * kBlockK, sw0 + dx, sh0 + dy, tc.n0);
+                }
+              }
+              __syncwarp();
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -233,38 +289,85 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             }
           }
         }
+        if (issuer) trace_ev(p, iter, 1);
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ B (weight) producer
+    {
+      const bool issuer = elect_one();
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+        const int n_row = (tile % p.tiles_n) * p.BN + rank * b_rows;
+        for (int k = 0; k < p.ksteps; ++k) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (issuer) {
+            if (kPair) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(b_bytes));
+              tma_load_2d_pair(&p.mapB, full0 + static_cast<uint32_t>(stage) * 8u, sB + stage * b_bytes, k * kBlockK, n_row);
+            } else {
+              mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(b_bytes));
+              tma_load_2d(&p.mapB, &full_bar[stage], sB + stage * b_bytes, k * kBlockK, n_row);
+            }
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBlockM, static_cast<uint32_t>(p.BN), false, false);
+    // The whole warp runs the (warp-uniform) loop and waits; one elected lane issues.  Keeping the control flow
+    // converged lets ptxas build the descriptors in uniform registers instead of moving them lane -> uniform per MMA.
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(p.BN), false, false);
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int iter = 0;
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
         for (int k = 0; k < p.ksteps; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (k == 0 && issuer) trace_ev(p, iter, 2);
           const uint64_t da = umma_desc_kmajor_sw128(sA_addr + stage * kABytes);
           const uint64_t db = umma_desc_kmajor_sw128(sB_addr + stage * b_bytes);
+          if (issuer) {
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                        (k | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+              if (kPair)
+                umma_f16_ss_pair(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                                 (k | kk) != 0 ? 1u : 0u);
+              else
+                umma_f16_ss(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                            (k | kk) != 0 ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+            if (kPair) umma_commit_pair(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (issuer) {
+          // accumulator complete -> epilogue warps (of both CTAs)
+          if (kPair) umma_commit_pair(&tmem_full[as], 3); else umma_commit(&tmem_full[as]);
+          trace_ev(p, iter, 3);
+        }
+        __syncwarp();
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -293,24 +396,35 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     uint8_t* my_out_row0 = sOut + row * 64;
     const uint8_t* my_res_row0 = sRes + row * 64;
     const int estep = p.egroups;                 // this group handles every estep-th chunk of the CTA's chunk stream
+    // accumulator hand-back: the MMA thread (leader CTA) waits on ITS tmem_empty barriers
+    uint32_t te_addr[2];
+    te_addr[0] = kPair ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
+    te_addr[1] = kPair ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : smem_u32(&tmem_empty[1]);
+    auto release_acc = [&](int a) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(te_addr[a]); else mbar_arrive(&tmem_empty[a]);
+      }
+    };
 
     // residual prefetch cursor: runs res_bufs chunks of this group ahead of the consumer, across tile boundaries
-    int pf_tile = blockIdx.x, pf_chunk = 0, pf_seq = 0;   // pf_seq: position in the CTA-wide chunk stream
+    int pf_tile = tile0, pf_chunk = 0, pf_seq = 0;   // pf_seq: position in the CTA-wide chunk stream
     uint32_t pf_count = 0;
     auto prefetch_residual = [&]() {
       while (pf_tile < p.num_tiles && (pf_seq % estep) != eg) {   // skip the other group's chunks
         ++pf_seq;
-        if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += gridDim.x; }
+        if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += tile_step; }
       }
       if (pf_tile >= p.num_tiles) return;
-      const TileCoord t = decode_tile(p, pf_tile);
+      const TileCoord t = decode_tile<kPair>(p, pf_tile, rank);
       const int col = t.n_blk * cols_per_tile + pf_chunk * kChunkCols;
       const int b = pf_count % p.res_bufs;
       mbar_expect_tx(&my_res_full[b], kChunkBytes);
       tma_load_4d(&p.mapRes, &my_res_full[b], sRes + b * kChunkBytes, col, t.w0, t.h0, t.n0);
       ++pf_count;
       ++pf_seq;
-      if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += gridDim.x; }
+      if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += tile_step; }
     };
     if (has_res_stage && leader && active) {
       for (int i = 0; i < p.res_bufs; ++i) prefetch_residual();
@@ -320,8 +434,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     uint32_t aphase = 0;
     uint32_t g = 0;    // chunks processed by THIS group so far (buffer indices derive from it)
     int seq = 0;       // position in the CTA-wide chunk stream
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    int iter = 0;
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
+      const TileCoord tc = decode_tile<kPair>(p, tile, rank);
       const int col_tile = tc.n_blk * cols_per_tile;
       // does this group own any chunk of this tile?  (uniform over the group)
       int first_c = (eg - (seq % estep) + estep) % estep;
@@ -366,12 +481,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if (leader && active) trace_ev(p, iter, 4 + 2 * eg);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
-      if (!has_work) {                             // nothing to read: release our share of the accumulator buffer
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      }
+      if (!has_work) release_acc(as);              // nothing to read: release our share of the accumulator buffer
       for (int c = first_c; has_work && c < nchunks; c += estep, ++g) {
         const int b = g % p.out_bufs;
         const int c0 = c * kChunkCols;
@@ -413,11 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
         }
-        if (c == last_c) {                         // our last read of this accumulator: hand our share back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        }
+        if (c == last_c) release_acc(as);          // our last read of this accumulator: hand our share back to the MMA warp
         if (has_res_stage) {
           const int rb_i = g % p.res_bufs;
           mbar_wait(&my_res_full[rb_i], (g / p.res_bufs) & 1);
@@ -458,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           if (has_res_stage) prefetch_residual();  // refill the residual buffer just consumed
         }
       }
+      if (leader && active) trace_ev(p, iter, 5 + 2 * eg);
       seq += nchunks;
       as ^= 1;
       if (as == 0) aphase ^= 1u;
@@ -467,9 +576,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     // ------------------------------------------------------------------ direct mode: warps 6..9 only hand-shake
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
       mbar_wait(&tmem_full[as], aphase);
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -488,8 +599,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
                       ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile<kPair>(p, tile, rank);
       const int w = tc.w0 + r_w, h = tc.h0 + r_h, n = tc.n0 + r_n;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.NB);
       const size_t m = (static_cast<size_t>(n) * p.H + h) * p.W + w;
@@ -563,33 +674,49 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // the peer may still read our operands / signal our barriers
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 1] = globaltimer_ns();
+    p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 3] = static_cast<unsigned long long>(clock64());
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if (kPair) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
-int pick_bn(int N_out, int tiles_m, int act, int sms) {
-  if (act == UDT_ACT_GEGLU) return kGegluTile;
+unsigned long long* g_trace_buf = nullptr;
+long long g_trace_bytes = 0;
+
+// Column-tile choice by a per-tile cost model calibrated on B200 (scripts/igemm_trace.py, scripts/micro/tma_rate.cu):
+// a K step (64 deep) costs max(MMA floor = 2*BN clk, operand ingest = (16 KB + B bytes) / ~73 B/clk); a CTA pair halves the
+// B bytes per CTA.  Tiles are processed in waves over the SMs (pairs: over SM pairs).
+int pick_bn(int N_out, int tiles_m, int ksteps, bool pair, int sms) {
   if (N_out <= 16) return 16;
   static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  const int units = pair ? sms / 2 : sms;
+  const int tm = pair ? (tiles_m + 1) / 2 : tiles_m;
   int best = 128;
   double best_cost = 1e30;
   for (int bn : cands) {
     const int tn = (N_out + bn - 1) / bn;
-    const long tiles = static_cast<long>(tn) * tiles_m;
-    const long waves = (tiles + sms - 1) / sms;
-    // per-tile time ~ MMA time (prop. to BN, floor at 64 because the A tile read is smem-bound) + fixed overhead
-    const double per_tile = (bn < 64 ? 64 : bn) + 24.0;
-    const double cost = static_cast<double>(waves) * per_tile;
+    const long tiles = static_cast<long>(tn) * tm;
+    const long waves = (tiles + units - 1) / units;
+    const double ingest = 224.0 + (pair ? 0.877 : 1.754) * bn;
+    const double kstep = (2.0 * bn > ingest) ? 2.0 * bn : ingest;
+    const double mainloop = ksteps * kstep;
+    const double epi = 400.0 + 14.0 * bn;
+    const double tile = (mainloop > epi ? mainloop : epi) + 300.0;
+    const double cost = static_cast<double>(waves) * tile + epi;
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;
@@ -598,9 +725,51 @@ int pick_bn(int N_out, int tiles_m, int act, int sms) {
   return best;
 }
 
+template <bool kPair>
+int launch_igemm(const IGemmParams& p, int grid, int smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(udt_igemm_kernel<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return udt_host::fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(igemm smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (kPair) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = 2;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  na += udt_host::pdl_attr(&attrs[na]);
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, udt_igemm_kernel<kPair>, p);
+  if (e != cudaSuccess) return udt_host::fail(UDT_ERR_LAUNCH, "udt_igemm launch: %s", cudaGetErrorString(e));
+  return UDT_OK;
+}
+
 }  // namespace
 
 extern "C" int udt_geglu_tile(void) { return kGegluTile; }
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+extern "C" int udt_debug_set_trace(void* buf, int64_t nbytes) {
+  g_trace_buf = reinterpret_cast<unsigned long long*>(buf);
+  g_trace_bytes = nbytes;
+  return kTraceStride;
+}
 
 extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   using namespace udt_host;
@@ -610,16 +779,10 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   const int nsrc = d->nsrc, NB = d->NB, H = d->H, W = d->W, N_out = d->N_out, act = d->act;
   if (nsrc < 1 || nsrc > 3) return fail(UDT_ERR_SHAPE, "udt_igemm: nsrc=%d (1..3)", nsrc);
   if (NB < 1 || H < 1 || W < 1 || N_out < 1) return fail(UDT_ERR_SHAPE, "udt_igemm: bad shape NB=%d H=%d W=%d N=%d", NB, H, W, N_out);
-  if (act == UDT_ACT_GEGLU && (N_out % (2 * 32) != 0 || N_out % kGegluTile != 0 || d->out_fp32 || d->residual || d->rowbias))
-    return fail(UDT_ERR_SHAPE, "udt_igemm: GEGLU needs N_out %% %d == 0, fp16 out, no residual/rowbias", kGegluTile);
+  const int geglu_tile = (act == UDT_ACT_GEGLU) ? (d->bn_hint > 0 ? d->bn_hint : kGegluTile) : 0;
+  if (act == UDT_ACT_GEGLU && ((geglu_tile != 128 && geglu_tile != 256) || N_out % geglu_tile != 0 || d->out_fp32 || d->residual || d->rowbias))
+    return fail(UDT_ERR_SHAPE, "udt_igemm: GEGLU needs a 128/256 column interleave (bn_hint), N_out %% tile == 0, fp16 out, no residual/rowbias");
   if (d->out == nullptr || d->weight == nullptr) return fail(UDT_ERR_SHAPE, "udt_igemm: null out / weight");
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(udt_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(igemm smem): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
 
   int max_stride = 1;
   for (int s = 0; s < nsrc; ++s) {
@@ -656,13 +819,19 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   p.tiles_nb = (NB + p.bn - 1) / p.bn;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_nb;
   const int sms = num_sms();
-  int BN = d->bn_hint > 0 ? d->bn_hint : pick_bn(N_out, tiles_m, act, sms);
+  int ksteps_est = 0;
+  for (int s = 0; s < nsrc; ++s) ksteps_est += d->src[s].taps * ((d->src[s].C + 63) / 64);
+  // CTA pairs (tcgen05 cta_group::2) whenever there are at least two M tiles and a real column tile
+  static const int pair_env = env_int("UDT_IGEMM_PAIR", 1);
+  bool pair = pair_env != 0 && tiles_m >= 2 && N_out > 16 && sms >= 2;
+  int BN = geglu_tile > 0 ? geglu_tile : (d->bn_hint > 0 ? d->bn_hint : pick_bn(N_out, tiles_m, ksteps_est, pair, sms));
   if (BN != 16 && (BN % 32 != 0 || BN < 32 || BN > 256)) return fail(UDT_ERR_SHAPE, "udt_igemm: BN=%d unsupported", BN);
-  if (act == UDT_ACT_GEGLU && BN != kGegluTile) return fail(UDT_ERR_SHAPE, "udt_igemm: GEGLU requires BN=%d", kGegluTile);
+  if (BN == 16) pair = false;
   p.BN = BN;
   p.N_out = N_out;
   p.tiles_n = (N_out + BN - 1) / BN;
-  p.num_tiles = tiles_m * p.tiles_n;
+  p.num_tiles = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n;
+  const int b_rows = pair ? BN / 2 : BN;
 
   int ktotal = 0;
   p.nseg = nsrc;
@@ -689,7 +858,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   const int ldw = d->ldw > 0 ? d->ldw : kdim_b;
   if (ldw < kdim_b) return fail(UDT_ERR_SHAPE, "udt_igemm: ldw=%d < K=%d (conv weights must be packed per 64-channel block)", ldw, kdim_b);
   rc = make_tmap_2d(&p.mapB, d->weight, static_cast<uint64_t>(kdim_b), static_cast<uint64_t>(N_out),
-                    static_cast<uint64_t>(ldw), 64, static_cast<uint32_t>(BN));
+                    static_cast<uint64_t>(ldw), 64, static_cast<uint32_t>(b_rows));
   if (rc != UDT_OK) return rc;
 
   // staged (TMA store) epilogue for fp16 outputs with a TMA-compatible layout; tiny / fp32 outputs store directly
@@ -713,7 +882,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
       p.res_bufs = short_k ? 3 : 2;
     }
     epi_bytes = p.egroups * ((p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes);
-    const int stage_b = kABytes + BN * kBlockK * 2;
+    const int stage_b = kABytes + b_rows * kBlockK * 2;
     if (short_k && (kSmemBudget - kCtrlBytes - 1024 - epi_bytes) / stage_b < 3) {
       // wide column tiles: keep at least 3 operand stages, fall back to the shallow single-group epilogue
       p.egroups = 1;
@@ -722,7 +891,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
       epi_bytes = (p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes;
     }
   }
-  const int stage_bytes = kABytes + BN * kBlockK * 2;
+  const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   int stages = (kSmemBudget - kCtrlBytes - 1024 - epi_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(UDT_ERR_SHAPE, "udt_igemm: tile does not fit shared memory");
@@ -743,12 +912,15 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
     dbg = e ? atoi(e) : 0;
   }
   p.debug = dbg;
+  p.trace = nullptr;
   if (dbg & 0xF00) {
     const int force = (dbg >> 8) & 0xF;
     if (force >= 2 && force <= stages) stages = force, p.stages = force;
   }
   const int smem = kCtrlBytes + 1024 + epi_bytes + stages * stage_bytes;
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  udt_igemm_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  return check_launch("udt_igemm");
+  const int units = pair ? sms / 2 : sms;
+  const int grid = (p.num_tiles < units ? p.num_tiles : units) * (pair ? 2 : 1);
+  if (g_trace_buf != nullptr && static_cast<long long>(grid) * kTraceStride * 8 <= g_trace_bytes) p.trace = g_trace_buf;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return pair ? launch_igemm<true>(p, grid, smem, st) : launch_igemm<false>(p, grid, smem, st);
 }

@@ -44,6 +44,7 @@ _PROTOTYPES = {
     "udt_sizeof_igemm_desc": (c_int32, []),
     "udt_geglu_tile": (c_int32, []),
     "udt_igemm": (c_int32, [POINTER(IGemmDesc), c_void_p]),
+    "udt_debug_set_trace": (c_int32, [c_void_p, c_int64]),
     "udt_groupnorm_ws_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "udt_groupnorm_nhwc": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                      c_void_p, c_float, c_int32, c_void_p, c_void_p]),

@@ -151,6 +151,9 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     m, k = x.shape
     n = weight.shape[0]
     n_log = n // 2 if act == UDT_ACT_GEGLU else n
+    if act == UDT_ACT_GEGLU and bn_hint == 0:
+        from .pack import GEGLU_TILE
+        bn_hint = GEGLU_TILE          # the column interleave the weight was packed with
     if out is None:
         out = torch.empty((m, n_log), device=x.device, dtype=torch.float32 if out_fp32 else torch.float16)
     return igemm([(x, k, x.stride(0), 1)], 1, 1, m, weight, n, out, out.stride(0), bias=bias, residual=residual,

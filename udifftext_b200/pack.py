@@ -6,7 +6,7 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-GEGLU_TILE = 128  # must equal udt_geglu_tile()
+GEGLU_TILE = 256  # must equal udt_geglu_tile(); passed to udt_igemm as bn_hint (128 is also accepted)
 
 
 def _pad64(n: int) -> int:
