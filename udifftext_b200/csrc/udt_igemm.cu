@@ -44,10 +44,11 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kCtrlBytes = 1024;
 constexpr int kGegluTile = 256;                      // preferred GEGLU weight interleave (128 is accepted via bn_hint)
 constexpr int kChunkCols = 32;                      // epilogue staging granularity: 32 fp16 columns = 64 B rows
-constexpr int kChunkBytes = kBlockM * kChunkCols * 2;  // 8 KB
+constexpr int kChunkBytes = kBlockM * kChunkCols * 2;  // 8 KB per 128-row chunk = 4 warp slabs
+constexpr int kSlabBytes = 32 * kChunkCols * 2;        // 2 KB: one warp's 32 rows x 32 fp16 columns
 constexpr int kBiasImgs = 4;                        // per-image bias rows staged per tile (tiles spanning more images
                                                     // read rowbias from global memory)
-constexpr int kBiasBytes = kBiasImgs * 256 * 4;     // 4 KB
+constexpr int kBiasBytes = 2 * kBiasImgs * 256 * 4; // 8 KB: double buffered (the next tile's rows are fetched a tile ahead)
 constexpr int kEpiBarrier = 1;                      // named barrier ids 1, 2: the two epilogue warpgroups
 constexpr int kMaxResBufs = 4;
 
@@ -62,6 +63,7 @@ struct IGemmParams {
   int32_t W, H, NB;
   int32_t bw, bh, bn;
   int32_t tiles_w, tiles_h, tiles_nb, tiles_n, num_tiles;
+  uint32_t mg_n, mg_w, mg_h;   // fast_div magic numbers of tiles_n, tiles_w, tiles_h
   int32_t N_out, BN, stages;
   const float* bias;
   const float* rowbias;
@@ -90,8 +92,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void trace_ev(const IGemmParams& p, int iter, int ev) {
-  if (p.trace != nullptr && iter < kTraceTiles)
+__device__ __forceinline__ void trace_ev(const IGemmParams& p, int iter, int ev, bool fine = false) {
+  if (p.trace != nullptr && iter < kTraceTiles && (((p.debug & 16) != 0) == fine || ev == 4))
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 4 + iter * kTraceEvents + ev] =
         static_cast<unsigned long long>(clock64());
 }
@@ -100,18 +102,25 @@ struct TileCoord {
   int w0, h0, n0, n_blk;
 };
 
+// n / d for n * d < 2^32 with magic = ceil(2^32 / d) (host: fast_div_magic)
+__device__ __forceinline__ int fast_div(int n, uint32_t magic, int d) {
+  return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic));
+}
+
 // `tile` counts (M tile or M-tile pair, N tile); `rank` = CTA rank within the pair (0 in single mode).  An odd tile
 // count leaves a phantom M tile whose image coordinate is out of range: TMA zero-fills its loads and clips its stores.
 template <bool kPair>
 __device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int tile, int rank) {
   TileCoord t;
-  t.n_blk = tile % p.tiles_n;
-  int m_blk = tile / p.tiles_n;
+  // exact division by multiply-high with host-computed magic numbers (a runtime integer division costs > 100 clk of
+  // dependent latency, and this runs on the critical path of every role once per tile / residual prefetch)
+  int m_blk = fast_div(tile, p.mg_n, p.tiles_n);
+  t.n_blk = tile - m_blk * p.tiles_n;
   if (kPair) m_blk = 2 * m_blk + rank;
-  int tw = m_blk % p.tiles_w;
-  int r = m_blk / p.tiles_w;
-  int th = r % p.tiles_h;
-  int tn = r / p.tiles_h;
+  const int r = fast_div(m_blk, p.mg_w, p.tiles_w);
+  const int tw = m_blk - r * p.tiles_w;
+  const int tn = fast_div(r, p.mg_h, p.tiles_h);
+  const int th = r - tn * p.tiles_h;
   t.w0 = tw * p.bw;
   t.h0 = th * p.bh;
   t.n0 = tn * p.bn;
@@ -183,8 +192,14 @@ __device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[
   for (int j = 0; j < cnt; ++j) o[j] = __float2half_rn(f[j]);
 }
 
-template <bool kPair>
+// kMode selects the epilogue that is compiled in (the hot loop carries no dead variants):
+//   0 staged, bias / staged per-image bias / residual      1 staged GEGLU
+//   2 staged, general (SiLU / ReLU / per-image bias of tiles spanning many images)      3 direct global stores
+template <bool kPair, int kMode>
 __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_constant__ IGemmParams p) {
+  constexpr bool kStaged = (kMode != 3);
+  constexpr bool kGeglu = (kMode == 1);
+  constexpr bool kGeneral = (kMode == 2);
   griddep_launch();   // PDL: the next kernel of the stream may start its prologue while this one runs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -195,14 +210,14 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;           // [2 groups][kMaxResBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2 * kMaxResBufs);
+  uint64_t* res_full = tmem_empty + 2;           // [8 epilogue warps][kMaxResBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8 * kMaxResBufs);
 
   // staged epilogue buffers (per epilogue group: out chunks, residual chunks, bias rows) sit between the control
   // block and the operand ring
-  const bool has_res_stage = p.staged && p.residual != nullptr;
+  const bool has_res_stage = kStaged && !kGeglu && p.residual != nullptr;
   const int group_bytes = (p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes;
-  const int epi_bytes = p.staged ? p.egroups * group_bytes : 0;
+  const int epi_bytes = kStaged ? p.egroups * group_bytes : 0;
 
   const int b_rows = kPair ? p.BN / 2 : p.BN;          // weight rows this CTA stages per K step
   const int b_bytes = b_rows * kBlockK * 2;
@@ -228,8 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kPair ? 16 : 8);   // 8 epilogue warps per CTA; the leader's copy collects both CTAs
     }
-    for (int s = 0; s < 2 * kMaxResBufs; ++s) mbar_init(&res_full[s], 1);
-    if (p.staged) {
+    for (int s = 0; s < 8 * kMaxResBufs; ++s) mbar_init(&res_full[s], 1);
+    if (kStaged) {
       tma_prefetch_desc(&p.mapOut);
       if (p.residual != nullptr) tma_prefetch_desc(&p.mapRes);
     }
@@ -372,29 +387,37 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
         if (as == 0) aphase ^= 1u;
       }
     }
-  } else if (p.staged) {
+  } else if (kStaged) {
     // ------------------------------------------------------------------ staged epilogue (warps 2..9, two groups)
+    // Every warp drains its own 32 accumulator rows on its own: tcgen05.ld (software pipelined, the next chunk's load
+    // flies while this one is finished) -> bias / activation / residual -> 64B-swizzled 2 KB slab in shared memory ->
+    // its own TMA slab store.  No CTA- or group-wide barrier per chunk (only the per-tile bias staging syncs a group).
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
     const int row = quarter * 32 + lane;
     const int eg = (warp - 2) >> 2;              // epilogue group 0 / 1
     const int et = threadIdx.x - 64 - eg * 128;  // 0..127 within the group
-    const bool leader = (et == 0);               // issues the group's TMA stores / residual prefetches
+    const bool issuer = elect_one();             // this warp's TMA thread (stores, residual prefetches)
+    const bool tracer = issuer && quarter == 0;
     const bool active = eg < p.egroups;          // with one group, warps 6..9 only keep the TMEM hand-shake going
     const uint32_t bar_id = kEpiBarrier + eg;
-    const bool geglu = (p.act == UDT_ACT_GEGLU);
+    constexpr bool geglu = kGeglu;
     const int cols_per_tile = geglu ? p.BN / 2 : p.BN;     // logical output columns per tile
     const int nchunks = cols_per_tile / kChunkCols;
     const int n_logical = geglu ? p.N_out / 2 : p.N_out;
     const int bwh = p.bw * p.bh;
     const int img_in_tile = row / bwh;           // which of the tile's images this row belongs to
-    const bool bias_staged_rb = (p.rowbias == nullptr) || (p.bn <= kBiasImgs);
-    const uint32_t swz = static_cast<uint32_t>((row >> 1) & 3);
-    uint8_t* sOut = base + kCtrlBytes + (active ? eg : 0) * group_bytes;
-    uint8_t* sRes = sOut + p.out_bufs * kChunkBytes;
-    float* sBias = reinterpret_cast<float*>(sRes + p.res_bufs * kChunkBytes);
-    uint64_t* my_res_full = res_full + eg * kMaxResBufs;
-    uint8_t* my_out_row0 = sOut + row * 64;
-    const uint8_t* my_res_row0 = sRes + row * 64;
+    const bool bias_staged_rb = !kGeneral || (p.rowbias == nullptr) || (p.bn <= kBiasImgs);
+    const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
+    // this warp's slab of the tile: rows [32*quarter, +32) = a {sbw, sbh, sbn} pixel box at (wq, hq, nq) inside the tile
+    const int r0 = quarter * 32;
+    const int wq = r0 % p.bw, hq = (r0 / p.bw) % p.bh, nq = r0 / bwh;
+    uint8_t* sGroup = base + kCtrlBytes + (active ? eg : 0) * group_bytes;
+    uint8_t* sOut = sGroup + quarter * (p.out_bufs + p.res_bufs) * kSlabBytes;     // [out_bufs][32 rows][64 B]
+    uint8_t* sRes = sOut + p.out_bufs * kSlabBytes;                                // [res_bufs][32 rows][64 B]
+    float* sBias = reinterpret_cast<float*>(sGroup + 4 * (p.out_bufs + p.res_bufs) * kSlabBytes);
+    uint64_t* my_res_full = res_full + (warp - 2) * kMaxResBufs;
+    uint8_t* my_out_row0 = sOut + lane * 64;
+    const uint8_t* my_res_row0 = sRes + lane * 64;
     const int estep = p.egroups;                 // this group handles every estep-th chunk of the CTA's chunk stream
     // accumulator hand-back: the MMA thread (leader CTA) waits on ITS tmem_empty barriers
     uint32_t te_addr[2];
@@ -408,101 +431,113 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       }
     };
 
-    // residual prefetch cursor: runs res_bufs chunks of this group ahead of the consumer, across tile boundaries
+    // residual prefetch cursor (issuer lane): runs res_bufs chunks of this warp ahead of the consumer, across tiles
     int pf_tile = tile0, pf_chunk = 0, pf_seq = 0;   // pf_seq: position in the CTA-wide chunk stream
-    uint32_t pf_count = 0;
+    int pf_b = 0;                                    // residual slab the next prefetch lands in
     auto prefetch_residual = [&]() {
-      while (pf_tile < p.num_tiles && (pf_seq % estep) != eg) {   // skip the other group's chunks
+      while (pf_tile < p.num_tiles && (pf_seq & (estep - 1)) != eg) {   // skip the other group's chunks (estep is 1 or 2)
         ++pf_seq;
         if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += tile_step; }
       }
       if (pf_tile >= p.num_tiles) return;
       const TileCoord t = decode_tile<kPair>(p, pf_tile, rank);
       const int col = t.n_blk * cols_per_tile + pf_chunk * kChunkCols;
-      const int b = pf_count % p.res_bufs;
-      mbar_expect_tx(&my_res_full[b], kChunkBytes);
-      tma_load_4d(&p.mapRes, &my_res_full[b], sRes + b * kChunkBytes, col, t.w0, t.h0, t.n0);
-      ++pf_count;
+      const int b = pf_b;
+      if (++pf_b == p.res_bufs) pf_b = 0;
+      mbar_expect_tx(&my_res_full[b], kSlabBytes);
+      tma_load_4d(&p.mapRes, &my_res_full[b], sRes + b * kSlabBytes, col, t.w0 + wq, t.h0 + hq, t.n0 + nq);
       ++pf_seq;
       if (++pf_chunk == nchunks) { pf_chunk = 0; pf_tile += tile_step; }
     };
-    if (has_res_stage && leader && active) {
+    if (has_res_stage && issuer && active) {
       for (int i = 0; i < p.res_bufs; ++i) prefetch_residual();
     }
 
+    // per-tile bias rows (+ per-image bias): fetched one tile ahead into registers, staged in a double-buffered smem row
+    float bv[2][kBiasImgs];
+    const int nimg = (p.rowbias != nullptr && bias_staged_rb) ? min(p.bn, kBiasImgs) : 1;
+    auto load_bias = [&](const TileCoord& t) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int cc = et + h2 * 128;              // column within the (packed) tile, < BN <= 256
+        const int gcol = t.n_blk * p.BN + cc;
+        const bool ok = (cc < p.BN) && (gcol < p.N_out);
+        const float b0 = (ok && p.bias != nullptr) ? __ldg(p.bias + gcol) : 0.0f;
+#pragma unroll
+        for (int im = 0; im < kBiasImgs; ++im) {
+          float v = b0;
+          if (ok && im < nimg && p.rowbias != nullptr && bias_staged_rb) {
+            const int img = min(t.n0 + im, p.NB - 1);
+            v += __ldg(p.rowbias + static_cast<size_t>(img) * p.ld_rowbias + gcol);
+          }
+          bv[h2][im] = v;
+        }
+      }
+    };
+    if (active && tile0 < p.num_tiles) load_bias(decode_tile<kPair>(p, tile0, rank));
+
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t g = 0;    // chunks processed by THIS group so far (buffer indices derive from it)
+    int ob = 0;                    // output slab the next chunk of this warp is staged in
+    int rb = 0;                    // residual slab / phase the next chunk of this warp reads
+    uint32_t rphase = 0;
     int seq = 0;       // position in the CTA-wide chunk stream
     int iter = 0;
+    const int esh = estep - 1;     // estep is 1 or 2: x % estep == x & esh, x / estep == x >> esh
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
       const TileCoord tc = decode_tile<kPair>(p, tile, rank);
       const int col_tile = tc.n_blk * cols_per_tile;
       // does this group own any chunk of this tile?  (uniform over the group)
-      int first_c = (eg - (seq % estep) + estep) % estep;
+      const int first_c = (eg - seq) & esh;
       const bool has_work = active && first_c < nchunks;
       int last_c = -1;
-      if (has_work) last_c = first_c + ((nchunks - 1 - first_c) / estep) * estep;
+      if (has_work) last_c = first_c + (((nchunks - 1 - first_c) >> esh) << esh);
       const float* my_bias = sBias;
-      if (has_work) {
-        // ---- stage bias (+ per-image bias) of this tile's columns: global loads fly while the MMAs finish
-        float bv[2][kBiasImgs];
-        const int nimg = (p.rowbias != nullptr && bias_staged_rb) ? min(p.bn, kBiasImgs) : 1;
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int cc = et + h2 * 128;              // column within the (packed) tile, < BN <= 256
-          const int gcol = tc.n_blk * p.BN + cc;
-          const bool ok = (cc < p.BN) && (gcol < p.N_out);
-          const float b0 = (ok && p.bias != nullptr) ? __ldg(p.bias + gcol) : 0.0f;
-#pragma unroll
-          for (int im = 0; im < kBiasImgs; ++im) {
-            float v = b0;
-            if (ok && im < nimg && p.rowbias != nullptr && bias_staged_rb) {
-              const int img = min(tc.n0 + im, p.NB - 1);
-              v += __ldg(p.rowbias + static_cast<size_t>(img) * p.ld_rowbias + gcol);
-            }
-            bv[h2][im] = v;
-          }
-        }
-        named_bar_sync(bar_id, 128);               // previous tile's readers of sBias are done
+      if (active) {
+        float* sb = sBias + (iter & 1) * (kBiasImgs * 256);
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int cc = et + h2 * 128;
           if (cc < p.BN) {
 #pragma unroll
             for (int im = 0; im < kBiasImgs; ++im)
-              if (im < nimg) sBias[im * 256 + cc] = bv[h2][im];
+              if (im < nimg) sb[im * 256 + cc] = bv[h2][im];
           }
         }
+        // one barrier per tile: this buffer was last read two tiles ago, and every thread passed the previous tile's
+        // barrier only after it had finished those reads
         named_bar_sync(bar_id, 128);
-        my_bias = sBias + ((p.rowbias != nullptr && bias_staged_rb) ? min(img_in_tile, kBiasImgs - 1) * 256 : 0);
+        if (tile + tile_step < p.num_tiles) load_bias(decode_tile<kPair>(p, tile + tile_step, rank));
+        my_bias = sb + ((p.rowbias != nullptr && bias_staged_rb) ? min(img_in_tile, kBiasImgs - 1) * 256 : 0);
       }
       const int my_img = min(tc.n0 + img_in_tile, p.NB - 1);
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      if (leader && active) trace_ev(p, iter, 4 + 2 * eg);
+      if (tracer && active) trace_ev(p, iter, 4 + 2 * eg);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
       if (!has_work) release_acc(as);              // nothing to read: release our share of the accumulator buffer
-      for (int c = first_c; has_work && c < nchunks; c += estep, ++g) {
-        const int b = g % p.out_bufs;
+      uint32_t v[32];
+      if (has_work && !geglu && !(p.debug & 8)) tmem_ld32(taddr + first_c * kChunkCols, v);   // prologue of the load pipeline
+      for (int c = first_c; has_work && c < nchunks; c += estep) {
+        const int b = ob;
+        if (++ob == p.out_bufs) ob = 0;
         const int c0 = c * kChunkCols;
         float f[32];
-        if (geglu) {
-          uint32_t vx[32], vg[32];
-          tmem_ld32(taddr + c0, vx);
+        if constexpr (geglu) {
+          uint32_t vg[32];
+          tmem_ld32(taddr + c0, v);
           tmem_ld32(taddr + p.BN / 2 + c0, vg);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(vx[j]) + my_bias[c0 + j];
+            const float x = __uint_as_float(v[j]) + my_bias[c0 + j];
             const float gt = __uint_as_float(vg[j]) + my_bias[p.BN / 2 + c0 + j];
             f[j] = x * gelu_erf_f(gt);
           }
         } else {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
+          if (!(p.debug & 8)) tmem_ld_wait_dep(v);   // this chunk's accumulators have landed in v[]
+          if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 0, true);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(my_bias + c0 + j);
@@ -511,25 +546,32 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
             f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
-          if (!bias_staged_rb) {
-            const float* rb = p.rowbias + static_cast<size_t>(my_img) * p.ld_rowbias + col_tile + c0;
+          if (c + estep < nchunks && !(p.debug & 8)) tmem_ld32(taddr + (c + estep) * kChunkCols, v);   // next chunk's load in flight
+          if constexpr (kGeneral) {
+            if (!bias_staged_rb) {
+              const float* rb = p.rowbias + static_cast<size_t>(my_img) * p.ld_rowbias + col_tile + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col_tile + c0 + j < p.N_out) f[j] += __ldg(rb + j);
-          }
-          if (p.act == UDT_ACT_SILU) {
+              for (int j = 0; j < 32; ++j)
+                if (col_tile + c0 + j < p.N_out) f[j] += __ldg(rb + j);
+            }
+            if (p.act == UDT_ACT_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-          } else if (p.act == UDT_ACT_RELU) {
+              for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+            } else if (p.act == UDT_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
           }
         }
-        if (c == last_c) release_acc(as);          // our last read of this accumulator: hand our share back to the MMA warp
+        if (geglu && c == last_c) release_acc(as);   // (pipelined path: released after the loop, no load in flight)
         if (has_res_stage) {
-          const int rb_i = g % p.res_bufs;
-          mbar_wait(&my_res_full[rb_i], (g / p.res_bufs) & 1);
-          const uint8_t* rrow = my_res_row0 + rb_i * kChunkBytes;
+          const int rb_i = rb;
+          mbar_wait(&my_res_full[rb_i], rphase);
+          if (++rb == p.res_bufs) {
+            rb = 0;
+            rphase ^= 1u;
+          }
+          const uint8_t* rrow = my_res_row0 + rb_i * kSlabBytes;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 rv = *reinterpret_cast<const uint4*>(rrow + ((static_cast<uint32_t>(q) ^ swz) << 4));
@@ -542,12 +584,17 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             }
           }
         }
-        // the TMA store that last used sOut[b] (out_bufs chunks ago) must have finished reading it
-        if (leader) {
-          if (p.out_bufs == 3) tma_store_wait_read<2>(); else tma_store_wait_read<1>();
+        if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 1, true);
+        // the slab store that last used sOut[b] (out_bufs chunks ago) must have finished reading it
+        if (issuer && !(p.debug & 32)) {
+          if (p.out_bufs == 4) tma_store_wait_read<3>();
+          else if (p.out_bufs == 3) tma_store_wait_read<2>();
+          else tma_store_wait_read<1>();
         }
-        named_bar_sync(bar_id, 128);
-        uint8_t* orow = my_out_row0 + b * kChunkBytes;
+        __syncwarp();
+        if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 2, true);
+        uint8_t* orow = my_out_row0 + b * kSlabBytes;
+        if (!(p.debug & 4))
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 ov;
@@ -557,21 +604,26 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           ov.w = pack_half2(f[q * 8 + 6], f[q * 8 + 7]);
           *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(q) ^ swz) << 4)) = ov;
         }
-        fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(bar_id, 128);               // chunk complete in sOut[b]; the residual buffer is consumed
-        if (leader) {
+        if (!(p.debug & 2)) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA engine
+        __syncwarp();                              // slab complete in sOut[b]; the residual slab is consumed
+        if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 3, true);
+        if (issuer) {
           const int col = col_tile + c0;
-          if (col < n_logical && !(p.debug & 1)) tma_store_4d(&p.mapOut, sOut + b * kChunkBytes, col, tc.w0, tc.h0, tc.n0);
-          tma_store_commit();
-          if (has_res_stage) prefetch_residual();  // refill the residual buffer just consumed
+          if (col < n_logical && !(p.debug & 1))
+            tma_store_4d(&p.mapOut, sOut + b * kSlabBytes, col, tc.w0 + wq, tc.h0 + hq, tc.n0 + nq);
+          if (!(p.debug & 64)) tma_store_commit();
+          if (has_res_stage) prefetch_residual();  // refill the residual slab just consumed
         }
+        if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 6, true);
       }
-      if (leader && active) trace_ev(p, iter, 5 + 2 * eg);
+      if (has_work && !geglu) release_acc(as);     // every load of this accumulator has completed
+      if (tracer && active) trace_ev(p, iter, 5 + 2 * eg);
+      if (tracer && eg == 0) trace_ev(p, iter, 7, true);
       seq += nchunks;
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
-    if (leader && active) tma_store_wait_all<0>();   // all output tiles written before the CTA retires
+    if (issuer && active) tma_store_wait_all<0>();   // all output slabs written before the CTA retires
   } else if (warp >= 6) {
     // ------------------------------------------------------------------ direct mode: warps 6..9 only hand-shake
     int as = 0;
@@ -725,11 +777,11 @@ int pick_bn(int N_out, int tiles_m, int ksteps, bool pair, int sms) {
   return best;
 }
 
-template <bool kPair>
+template <bool kPair, int kMode>
 int launch_igemm(const IGemmParams& p, int grid, int smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(udt_igemm_kernel<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(udt_igemm_kernel<kPair, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return udt_host::fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(igemm smem): %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -751,7 +803,7 @@ int launch_igemm(const IGemmParams& p, int grid, int smem, cudaStream_t st) {
   na += udt_host::pdl_attr(&attrs[na]);
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, udt_igemm_kernel<kPair>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, udt_igemm_kernel<kPair, kMode>, p);
   if (e != cudaSuccess) return udt_host::fail(UDT_ERR_LAUNCH, "udt_igemm launch: %s", cudaGetErrorString(e));
   return UDT_OK;
 }
@@ -832,6 +884,16 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   p.tiles_n = (N_out + BN - 1) / BN;
   p.num_tiles = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n;
   const int b_rows = pair ? BN / 2 : BN;
+  {
+    auto magic = [](int dv) { return dv <= 1 ? 0u : static_cast<uint32_t>(((1ull << 32) + dv - 1) / dv); };
+    p.mg_n = magic(p.tiles_n);
+    p.mg_w = magic(p.tiles_w);
+    p.mg_h = magic(p.tiles_h);
+    const unsigned long long worst = static_cast<unsigned long long>(2 * p.num_tiles + 2) *
+        static_cast<unsigned long long>(p.tiles_n > p.tiles_w ? (p.tiles_n > p.tiles_h ? p.tiles_n : p.tiles_h)
+                                                              : (p.tiles_w > p.tiles_h ? p.tiles_w : p.tiles_h));
+    if (worst >= (1ull << 32)) return fail(UDT_ERR_SHAPE, "udt_igemm: problem too large for the tile decoder");
+  }
 
   int ktotal = 0;
   p.nseg = nsrc;
@@ -868,7 +930,11 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   p.staged = (!d->out_fp32 && BN >= 32 && aligned16 && n_logical >= 8) ? 1 : 0;
   int epi_bytes = 0;
   if (p.staged) {
-    rc = make_tmap_nhwc_c32(&p.mapOut, d->out, static_cast<uint64_t>(n_logical), W, H, NB, d->ldo, p.bw, p.bh, p.bn);
+    // every epilogue warp stores its own 32-row slab of the tile: a {sbw, sbh, sbn} pixel box
+    const int sbw = p.bw < 32 ? p.bw : 32;
+    const int sbh = p.bh < 32 / sbw ? p.bh : 32 / sbw;
+    const int sbn = 32 / (sbw * sbh);
+    rc = make_tmap_nhwc_c32(&p.mapOut, d->out, static_cast<uint64_t>(n_logical), W, H, NB, d->ldo, sbw, sbh, sbn);
     if (rc != UDT_OK) return rc;
     // short-K GEMMs are epilogue-bound: two epilogue warpgroups and deeper chunk buffering; long-K tiles hide a
     // single group's epilogue behind the mainloop and keep the shared memory for operand stages instead
@@ -877,7 +943,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
     p.out_bufs = short_k ? 3 : 2;
     p.res_bufs = 0;
     if (d->residual != nullptr) {
-      rc = make_tmap_nhwc_c32(&p.mapRes, d->residual, static_cast<uint64_t>(n_logical), W, H, NB, d->ldr, p.bw, p.bh, p.bn);
+      rc = make_tmap_nhwc_c32(&p.mapRes, d->residual, static_cast<uint64_t>(n_logical), W, H, NB, d->ldr, sbw, sbh, sbn);
       if (rc != UDT_OK) return rc;
       p.res_bufs = short_k ? 3 : 2;
     }
@@ -922,5 +988,20 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * (pair ? 2 : 1);
   if (g_trace_buf != nullptr && static_cast<long long>(grid) * kTraceStride * 8 <= g_trace_bytes) p.trace = g_trace_buf;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return pair ? launch_igemm<true>(p, grid, smem, st) : launch_igemm<false>(p, grid, smem, st);
+  int mode = 3;
+  if (p.staged) {
+    if (act == UDT_ACT_GEGLU) mode = 1;
+    else if (act != UDT_ACT_NONE || (p.rowbias != nullptr && p.bn > kBiasImgs)) mode = 2;
+    else mode = 0;
+  }
+  switch (mode * 2 + (pair ? 1 : 0)) {
+    case 0: return launch_igemm<false, 0>(p, grid, smem, st);
+    case 1: return launch_igemm<true, 0>(p, grid, smem, st);
+    case 2: return launch_igemm<false, 1>(p, grid, smem, st);
+    case 3: return launch_igemm<true, 1>(p, grid, smem, st);
+    case 4: return launch_igemm<false, 2>(p, grid, smem, st);
+    case 5: return launch_igemm<true, 2>(p, grid, smem, st);
+    case 6: return launch_igemm<false, 3>(p, grid, smem, st);
+    default: return launch_igemm<true, 3>(p, grid, smem, st);
+  }
 }
