@@ -11,14 +11,20 @@ from udifftext_b200 import ops, pack  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=3):
+    """device time per launch inside a CUDA graph of `iters` back-to-back launches (no host launch cost)"""
     for _ in range(warm):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     s = torch.cuda.Event(enable_timing=True)
     e = torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e.record()
     torch.cuda.synchronize()
     return s.elapsed_time(e) / iters
@@ -43,7 +49,8 @@ def main():
         y = torch.empty((m, n), device=dev, dtype=torch.float16)
         ms = timeit(lambda: ops.linear(x, w, out=y))
         out.append({"op": "linear", "m": m, "k": k, "n": n, "ms": round(ms, 4), "tflops": round(2.0 * m * k * n / ms / 1e9, 1)})
-        ms = timeit(lambda: torch.matmul(x, w.t()))
+        yy = torch.empty((m, n), device=dev, dtype=torch.float16)
+        ms = timeit(lambda: torch.matmul(x, w.t(), out=yy))
         out.append({"op": "cublas", "m": m, "k": k, "n": n, "ms": round(ms, 4), "tflops": round(2.0 * m * k * n / ms / 1e9, 1)})
     for n, heads in [(4096, 5), (1024, 10), (256, 20)]:
         c = heads * 64
@@ -52,7 +59,7 @@ def main():
         ms = timeit(lambda: ops.fmha(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], nb, n, n, heads, 0.125, out=o))
         fl = 4.0 * nb * heads * n * n * 64
         out.append({"op": "fmha", "nb": nb, "n": n, "heads": heads, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)})
-    for hw, c in [(4096, 320), (1024, 640), (256, 1280)]:
+    for hw, c in [(4096, 320), (4096, 640), (1024, 640), (1024, 1280), (256, 1280), (256, 2560), (64, 1280), (64, 2560)]:
         x = torch.randn((nb, hw, c), device=dev).half()
         g = torch.ones(c, device=dev)
         b = torch.zeros(c, device=dev)

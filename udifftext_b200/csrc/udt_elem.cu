@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(kXaThreads) xattn_small_l_kernel(const __half*
                                                                    __half* __restrict__ o, float* __restrict__ probs,
                                                                    int N, int L, int heads, int ldq, int ldkv, int ldo,
                                                                    float scale) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   __shared__ float sk[kXaMaxL * 64];
   __shared__ float sv[kXaMaxL * 64];
   const int b = blockIdx.z;
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(kXaThreads) xattn_small_l_kernel(const __half*
 // out fp16 [B*L, D] = emb[idx[b,l], :] + pe[l, :]
 __global__ void label_embed_kernel(const int32_t* __restrict__ idx, const float* __restrict__ emb,
                                    const float* __restrict__ pe, __half* __restrict__ out, int rows, int L, int D) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const size_t total = static_cast<size_t>(rows) * D;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -123,6 +127,8 @@ constexpr int kMhaThreads = 128;
 
 __global__ void __launch_bounds__(kMhaThreads) mha_small_kernel(const __half* __restrict__ qkv, __half* __restrict__ o,
                                                                 int L, int heads, int dh, int ld, int ldo, float scale) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   __shared__ __half sq[kMhaMaxL * kMhaMaxD];
   __shared__ __half sk[kMhaMaxL * kMhaMaxD];
   __shared__ __half sv[kMhaMaxL * kMhaMaxD];
@@ -171,6 +177,8 @@ constexpr int kSmThreads = 256;
 constexpr int kSmMaxVec = 8;  // 256 threads * 8 vec * 8 halves = 16384 columns
 
 __global__ void __launch_bounds__(kSmThreads) softmax_rows_kernel(__half* __restrict__ x, int cols, int ld, float scale) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   __shared__ float red[kSmThreads / 32];
   __half* xr = x + static_cast<size_t>(blockIdx.x) * ld;
   const int VC = cols / 8;
@@ -242,6 +250,8 @@ __global__ void __launch_bounds__(kSmThreads) softmax_rows_kernel(__half* __rest
 __global__ void cfg_pack_kernel(const float* __restrict__ x, const float* __restrict__ cat_uc,
                                 const float* __restrict__ cat_c, __half* __restrict__ out, int B, int HW,
                                 const float* __restrict__ c_in_dev) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 2B*HW pixels
   const int total = 2 * B * HW;
   if (idx >= total) return;
@@ -273,6 +283,8 @@ __global__ void cfg_pack_kernel(const float* __restrict__ x, const float* __rest
 // x[B,4,HW] (NCHW) += dsigma * (eps_u + s*(eps_c - eps_u)); eps2b fp32 NHWC [2B,HW,4]
 __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps, int B, int HW, float s,
                                  const float* __restrict__ dsigma_dev) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = B * HW;
   if (idx >= total) return;
@@ -296,6 +308,8 @@ __global__ void vae_sample_pack_kernel(const float* __restrict__ moments, int ld
                                        const float* __restrict__ noise_uc, const float* __restrict__ mask,
                                        float* __restrict__ cat_c, float* __restrict__ cat_uc, int B, int h, int w,
                                        float scale) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = h * w;
   if (idx >= B * HW) return;
@@ -325,6 +339,8 @@ __global__ void vae_sample_pack_kernel(const float* __restrict__ moments, int ld
 __global__ void pointwise_affine_kernel(const float* __restrict__ x, const float* __restrict__ Wm,
                                         const float* __restrict__ bias, __half* __restrict__ out, int B, int HW, int Cin,
                                         int Cout, int Cpad, float in_scale) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * HW) return;
   const int b = idx / HW, p = idx % HW;
@@ -346,6 +362,8 @@ __global__ void pointwise_affine_kernel(const float* __restrict__ x, const float
 
 // ---------------------------------------------------------------------------------------------- movement
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int NB, int H, int W, int VC) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const size_t total = static_cast<size_t>(NB) * (2 * H) * (2 * W) * VC;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -362,6 +380,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 // out[(n,oy,ox), tap*C + c] = x[n, oy*stride - pad_lo + ky, ox*stride - pad_lo + kx, c]; columns >= 9*C zero.
 __global__ void im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ out, int NB, int H, int W, int C,
                                  int ld, int stride, int pad_lo, int Ho, int Wo, int Kpad) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const size_t total = static_cast<size_t>(NB) * Ho * Wo * Kpad;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -383,6 +403,8 @@ __global__ void im2col3x3_kernel(const __half* __restrict__ x, __half* __restric
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restrict__ y, int NB, int C, int HW, int Cpad) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const size_t total = static_cast<size_t>(NB) * HW * Cpad;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -396,6 +418,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restr
 
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int is_f32, float* __restrict__ y, int NB, int C, int HW,
                                     int ld, float scale, float shift, int clamp01) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const size_t total = static_cast<size_t>(NB) * C * HW;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -431,7 +455,7 @@ extern "C" int udt_xattn_small_l(const void* q, const void* kc, const void* vc, 
   if (L < 1 || L > kXaMaxL) return fail(UDT_ERR_SHAPE, "udt_xattn_small_l: L=%d (1..%d)", L, kXaMaxL);
   if (ldq % 8 || ldo % 8) return fail(UDT_ERR_ALIGN, "udt_xattn_small_l: ldq/ldo must be multiples of 8");
   dim3 grid((N + kXaThreads - 1) / kXaThreads, heads, B);
-  xattn_small_l_kernel<<<grid, kXaThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(xattn_small_l_kernel, dim3(grid), dim3(kXaThreads), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(kc), reinterpret_cast<const __half*>(vc),
       reinterpret_cast<__half*>(o), probs, N, L, heads, ldq, ldkv, ldo, scale);
   return check_launch("udt_xattn_small_l");
@@ -443,7 +467,7 @@ extern "C" int udt_label_embed(const int32_t* idx, const float* emb, const float
   if (rc != UDT_OK) return rc;
   if (rows < 1 || L < 1 || D < 1) return fail(UDT_ERR_SHAPE, "udt_label_embed: rows=%d L=%d D=%d", rows, L, D);
   const size_t total = static_cast<size_t>(rows) * D;
-  label_embed_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(label_embed_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       idx, emb, pe, reinterpret_cast<__half*>(out), rows, L, D);
   return check_launch("udt_label_embed");
 }
@@ -455,7 +479,7 @@ extern "C" int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int
   if (L < 1 || L > kMhaMaxL || dh < 1 || dh > kMhaMaxD || B < 1 || heads < 1 || ld < 3 * heads * dh)
     return fail(UDT_ERR_SHAPE, "udt_mha_small: L=%d (<=%d) dh=%d (<=%d) ld=%d", L, kMhaMaxL, dh, kMhaMaxD, ld);
   dim3 grid(heads, B);
-  mha_small_kernel<<<grid, kMhaThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(mha_small_kernel, dim3(grid), dim3(kMhaThreads), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(o), L, heads, dh, ld, ldo, scale);
   return check_launch("udt_mha_small");
 }
@@ -465,7 +489,7 @@ extern "C" int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld,
   if (rc != UDT_OK) return rc;
   if (cols % 8 || ld % 8 || cols > kSmThreads * kSmMaxVec * 8 || cols < 8)
     return fail(UDT_ERR_SHAPE, "udt_softmax_rows: cols=%d ld=%d unsupported", cols, ld);
-  softmax_rows_kernel<<<rows, kSmThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<__half*>(x), cols,
+  udt_host::launch_pdl(softmax_rows_kernel, dim3(rows), dim3(kSmThreads), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__half*>(x), cols,
                                                                                        ld, scale);
   return check_launch("udt_softmax_rows");
 }
@@ -476,7 +500,7 @@ extern "C" int udt_cfg_pack(const float* x, const float* concat_uc, const float*
   if (rc != UDT_OK) return rc;
   if (B < 1 || HW < 1 || c_in_dev == nullptr) return fail(UDT_ERR_SHAPE, "udt_cfg_pack: B=%d HW=%d", B, HW);
   const int total = 2 * B * HW;
-  cfg_pack_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(cfg_pack_kernel, dim3((total + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, concat_uc, concat_c, reinterpret_cast<__half*>(unet_in), B, HW, c_in_dev);
   return check_launch("udt_cfg_pack");
 }
@@ -487,7 +511,7 @@ extern "C" int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32
   if (rc != UDT_OK) return rc;
   if (B < 1 || HW < 1 || dsigma_dev == nullptr) return fail(UDT_ERR_SHAPE, "udt_cfg_euler_step: B=%d HW=%d", B, HW);
   const int total = B * HW;
-  cfg_euler_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, eps2b, B, HW, cfg_scale,
+  udt_host::launch_pdl(cfg_euler_kernel, dim3((total + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), x, eps2b, B, HW, cfg_scale,
                                                                                           dsigma_dev);
   return check_launch("udt_cfg_euler_step");
 }
@@ -499,7 +523,7 @@ extern "C" int udt_vae_sample_pack(const float* moments, int32_t ld_moments, con
   if (rc != UDT_OK) return rc;
   if (B < 1 || h < 1 || w < 1 || ld_moments < 8) return fail(UDT_ERR_SHAPE, "udt_vae_sample_pack: B=%d h=%d w=%d ld=%d", B, h, w, ld_moments);
   const int total = B * h * w;
-  vae_sample_pack_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(vae_sample_pack_kernel, dim3((total + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       moments, ld_moments, noise_c, noise_uc, mask, concat_c, concat_uc, B, h, w, scale_factor);
   return check_launch("udt_vae_sample_pack");
 }
@@ -511,7 +535,7 @@ extern "C" int udt_pointwise_affine(const float* x, const float* Wm, const float
   if (B < 1 || HW < 1 || Cin < 1 || Cin > 8 || Cout < 1 || Cout > Cpad)
     return fail(UDT_ERR_SHAPE, "udt_pointwise_affine: Cin=%d (1..8) Cout=%d Cpad=%d", Cin, Cout, Cpad);
   const int total = B * HW;
-  pointwise_affine_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(pointwise_affine_kernel, dim3((total + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, Wm, bias, reinterpret_cast<__half*>(out), B, HW, Cin, Cout, Cpad, in_scale);
   return check_launch("udt_pointwise_affine");
 }
@@ -521,7 +545,7 @@ extern "C" int udt_upsample2x_nhwc(const void* x, void* y, int32_t NB, int32_t H
   if (rc != UDT_OK) return rc;
   if (C % 8) return fail(UDT_ERR_SHAPE, "udt_upsample2x_nhwc: C=%d not a multiple of 8", C);
   const size_t total = static_cast<size_t>(NB) * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), NB, H, W, C / 8);
   return check_launch("udt_upsample2x_nhwc");
 }
@@ -532,7 +556,7 @@ extern "C" int udt_im2col3x3_nhwc(const void* x, void* out, int32_t NB, int32_t 
   if (rc != UDT_OK) return rc;
   if (Kpad < 9 * C || Kpad % 8) return fail(UDT_ERR_SHAPE, "udt_im2col3x3_nhwc: Kpad=%d < 9*C=%d", Kpad, 9 * C);
   const size_t total = static_cast<size_t>(NB) * Ho * Wo * Kpad;
-  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(im2col3x3_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), NB, H, W, C, ld, stride, pad_lo, Ho, Wo, Kpad);
   return check_launch("udt_im2col3x3_nhwc");
 }
@@ -542,7 +566,7 @@ extern "C" int udt_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t NB, int
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
   const size_t total = static_cast<size_t>(NB) * HW * Cpad;
-  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(nchw_to_nhwc_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__half*>(y), NB, C, HW, Cpad);
   return check_launch("udt_nchw_f32_to_nhwc_f16");
 }
@@ -552,7 +576,7 @@ extern "C" int udt_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* y, 
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
   const size_t total = static_cast<size_t>(NB) * C * HW;
-  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, x_is_fp32, y, NB, C, HW, ld, scale, shift, clamp01);
   return check_launch("udt_nhwc_to_nchw_f32");
 }

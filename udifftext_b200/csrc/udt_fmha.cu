@@ -47,6 +47,8 @@ constexpr int kOffP = kOffV + kKvStages * kTileBytes;
 constexpr int kSmemBytes = kOffP + 2 * kPBytes + 1024;
 
 __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_constant__ FmhaParams p) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -313,6 +315,6 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Nq + 2 * kTile - 1) / (2 * kTile), heads, B);
-  udt_fmha_kernel<<<grid, kThreads, kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  udt_host::launch_pdl(udt_fmha_kernel, dim3(grid), dim3(kThreads), kSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("udt_fmha_fwd");
 }

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 
 #include "../../include/udt_api.h"
 
@@ -20,6 +21,21 @@ int arch();                           // compute capability * 10 of the current 
 // Programmatic dependent launch (every kernel of this library executes griddepcontrol.wait before it touches
 // global memory): fills one launch attribute and returns 1, or returns 0 when disabled (UDT_PDL=0).
 int pdl_attr(cudaLaunchAttribute* attr);
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.numAttrs = pdl_attr(attr);
+  cfg.attrs = attr;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through check_launch()
+}
 
 // 2-D fp16 tensor map, dim0 = contiguous (cols), box = {box0, box1}, 128B swizzle.
 int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box0,

@@ -1,6 +1,12 @@
 // udt_norm.cu — K1 GroupNorm(+SiLU) and K6 LayerNorm on NHWC fp16 (HBM-bound kernels, fp32/fp64 statistics).
 //
-// GroupNorm runs as two coalesced passes over the pixel-major tensor:
+// GroupNorm has two schedules:
+//   one pass  (a sample's tensor fits the shared memory of a cluster of <= 8 CTAs, i.e. every UNet level except the
+//              64x64 one at >= 320 channels): each CTA of the cluster owns a slab of pixels, loads it ONCE into shared
+//              memory while accumulating per-channel sums, the CTAs exchange their per-group partial sums through
+//              distributed shared memory in a fixed order (deterministic), then normalise out of shared memory.
+//              One launch, 4 B/element of traffic.
+//   two pass  (large tensors) as two coalesced passes over the pixel-major tensor:
 //   pass 1 (stats)  : each CTA owns a slab of pixels of one image, every thread keeps per-channel partial
 //                     sums for a fixed 8-channel vector (16-byte loads), partials are folded per channel in
 //                     shared memory, then per group, and added to an fp64 [image, group] accumulator;
@@ -9,6 +15,7 @@
 // UNet skip concatenation without materialising th.cat.
 #include "udt_common.cuh"
 #include "udt_host.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -47,8 +54,33 @@ __device__ __forceinline__ void gn_accum(const uint4& v, float (&s)[8], float (&
   }
 }
 
+// SiLU with one MUFU op: x * sigmoid(x) = 0.5 x (1 + tanh(0.5 x)); tanh.approx error (2^-11) is below fp16 resolution
+__device__ __forceinline__ float silu_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return 0.5f * x * (1.0f + t);
+}
+
+// fold per-channel partial sums [rpi][C] of group g with `nl` cooperating lanes (lane j of the group), fp64, fixed order
+__device__ __forceinline__ void gn_group_fold(const float* ps, const float* pq, int rpi, int C, int cpg, int g, int j, int nl,
+                                              double& ds, double& dq) {
+  ds = 0.0;
+  dq = 0.0;
+  for (int rr = 0; rr < rpi; ++rr)
+    for (int cc = j; cc < cpg; cc += nl) {
+      ds += static_cast<double>(ps[rr * C + g * cpg + cc]);
+      dq += static_cast<double>(pq[rr * C + g * cpg + cc]);
+    }
+  for (int o = nl >> 1; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+}
+
 // pass 1: deterministic per-CTA partial statistics (no atomics anywhere)
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   extern __shared__ float sm[];  // [rpi][C] sums, then [rpi][C] sums of squares
   const int n = blockIdx.y;
   const int row0 = blockIdx.x * a.rows_per_cta;
@@ -86,21 +118,22 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
   }
   __syncthreads();
   const int cpg = a.C / a.groups;
-  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-    double ds = 0.0, dq = 0.0;
-    for (int rr = 0; rr < rpi; ++rr)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        ds += static_cast<double>(s_sum[rr * a.C + c]);
-        dq += static_cast<double>(s_sq[rr * a.C + c]);
-      }
-    double* st = a.partial + ((static_cast<size_t>(n) * a.groups + g) * a.chunks + blockIdx.x) * 2;
-    st[0] = ds;
-    st[1] = dq;
+  {
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;   // 8 lanes per group (256 threads, <= 32 groups)
+    double ds, dq;
+    gn_group_fold(s_sum, s_sq, rpi, a.C, cpg, min(g, a.groups - 1), j, 8, ds, dq);
+    if (j == 0 && g < a.groups) {
+      double* st = a.partial + ((static_cast<size_t>(n) * a.groups + g) * a.chunks + blockIdx.x) * 2;
+      st[0] = ds;
+      st[1] = dq;
+    }
   }
 }
 
 // pass 2: fold the partials in a fixed order, then y = x * A[c] + B[c] (+SiLU) with per-channel A/B in smem
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   extern __shared__ float sm[];  // A[C], B[C]
   __shared__ double s_red[kGnMaxGroups][8][2];
   __shared__ float s_mean[kGnMaxGroups];
@@ -188,7 +221,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
         o[7] = fmaf(f3.y, A1.w, B1.w);
         if (a.silu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = __fdividef(o[j], 1.0f + __expf(-o[j]));
+          for (int j = 0; j < 8; ++j) o[j] = silu_tanh(o[j]);
         }
         uint4 ov;
         ov.x = pack_half2(o[0], o[1]);
@@ -199,6 +232,138 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
       }
     }
   }
+}
+
+
+constexpr int kGn1Threads = 512;
+
+// one-pass GroupNorm: grid (S, NB), cluster (S, 1, 1); CTA `rank` of a cluster owns rows [rank*R, rank*R + R) of sample n
+__global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a) {
+  griddep_launch();
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __shared__ double s_part[kGnMaxGroups][2];
+  __shared__ float s_mean[kGnMaxGroups];
+  __shared__ float s_rstd[kGnMaxGroups];
+  const int n = blockIdx.y;
+  const int rank = blockIdx.x;
+  const int S = gridDim.x;
+  const int R = a.rows_per_cta;
+  const int row0 = rank * R;
+  const int nrows = max(0, min(a.HW, row0 + R) - row0);
+  const int VC = a.C / 8;                       // <= 512 (C <= 4096)
+  const int rpi = kGn1Threads / VC;             // row lanes
+  const int r = threadIdx.x / VC;
+  const int vc = threadIdx.x - r * VC;
+  const bool act = r < rpi;
+  uint4* slab = reinterpret_cast<uint4*>(gsm);                       // [R][VC] 16-byte vectors
+  float* ps = reinterpret_cast<float*>(gsm + static_cast<size_t>(R) * a.C * 2);   // [rpi][C]
+  float* pq = ps + rpi * a.C;
+  const int cpg = a.C / a.groups;
+  const size_t pix0 = static_cast<size_t>(n) * a.HW + row0;
+
+  // the slab is fetched with bulk asynchronous copies (one per row and source): the whole slab is in flight at once
+  __shared__ uint64_t s_bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  griddep_wait();
+  if (threadIdx.x == 0) mbar_expect_tx(&s_bar, static_cast<uint32_t>(nrows) * static_cast<uint32_t>(a.C) * 2u);
+  for (int row = threadIdx.x; row < nrows; row += kGn1Threads) {
+    uint8_t* dst = gsm + static_cast<size_t>(row) * a.C * 2;
+    bulk_load_1d(dst, a.x0 + (pix0 + row) * a.C0, static_cast<uint32_t>(a.C0) * 2u, &s_bar);
+    if (a.C1 > 0) bulk_load_1d(dst + a.C0 * 2, a.x1 + (pix0 + row) * a.C1, static_cast<uint32_t>(a.C1) * 2u, &s_bar);
+  }
+  mbar_wait(&s_bar, 0);
+  if (act) {
+    float sv[8], qv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sv[j] = qv[j] = 0.0f;
+    for (int row = r; row < nrows; row += rpi) gn_accum(slab[row * VC + vc], sv, qv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ps[r * a.C + vc * 8 + j] = sv[j];
+      pq[r * a.C + vc * 8 + j] = qv[j];
+    }
+  }
+  __syncthreads();
+  {
+    const int g = threadIdx.x >> 4, j = threadIdx.x & 15;   // 16 lanes per group (512 threads, <= 32 groups)
+    double ds, dq;
+    gn_group_fold(ps, pq, rpi, a.C, cpg, min(g, a.groups - 1), j, 16, ds, dq);
+    if (j == 0 && g < a.groups) {
+      s_part[g][0] = ds;
+      s_part[g][1] = dq;
+    }
+  }
+  cluster_sync_all();
+  if (threadIdx.x < a.groups) {
+    const uint32_t base = smem_u32(&s_part[threadIdx.x][0]);
+    double ds = 0.0, dq = 0.0;
+    for (int rk = 0; rk < S; ++rk) {               // fixed order over the cluster: deterministic
+      const uint32_t ra = mapa_u32(base, static_cast<uint32_t>(rk));
+      ds += ld_shared_cluster_f64(ra);
+      dq += ld_shared_cluster_f64(ra + 8);
+    }
+    const double cnt = static_cast<double>(a.HW) * cpg;
+    const double mean = ds / cnt;
+    double var = dq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+  cluster_sync_all();   // remote reads of s_part are complete before any CTA may exit; also publishes s_mean / s_rstd
+  if (act) {
+    float A[8], B[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = vc * 8 + j;
+      const int g = c / cpg;
+      A[j] = s_rstd[g] * __ldg(a.gamma + c);
+      B[j] = __ldg(a.beta + c) - s_mean[g] * A[j];
+    }
+    for (int row = r; row < nrows; row += rpi) {
+      const uint4 v = slab[row * VC + vc];
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        o[2 * j] = fmaf(f.x, A[2 * j], B[2 * j]);
+        o[2 * j + 1] = fmaf(f.y, A[2 * j + 1], B[2 * j + 1]);
+      }
+      if (a.silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = silu_tanh(o[j]);
+      }
+      uint4 ov;
+      ov.x = pack_half2(o[0], o[1]);
+      ov.y = pack_half2(o[2], o[3]);
+      ov.z = pack_half2(o[4], o[5]);
+      ov.w = pack_half2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(a.y + (pix0 + row) * a.C + vc * 8) = ov;
+    }
+  }
+}
+
+constexpr int kGn1SlabBudget = 184 * 1024;   // + <= 32 KB of partial sums + static smem < 227 KB
+
+// cluster size of the one-pass schedule for this problem, 0 = use the two-pass schedule
+inline int gn_onepass_cluster(int NB, int HW, int C) {
+  if (C / 8 > kGn1Threads) return 0;
+  int s_fit = 0;
+  for (int s = 1; s <= 8; s <<= 1) {
+    const long slab = static_cast<long>((HW + s - 1) / s) * C * 2;
+    if (slab <= kGn1SlabBudget) {
+      s_fit = s;
+      break;
+    }
+  }
+  if (s_fit == 0) return 0;
+  int s = s_fit;
+  while (s < 8 && NB * s < 96 && 2 * s <= HW) s <<= 1;   // spread small problems over more SMs
+  return s;
 }
 
 inline int gn_rows_per_cta(int C, int HW) {
@@ -215,6 +380,8 @@ constexpr int kLnMaxVec = 8;  // C <= 32 * 8 * 8 = 2048 kept in registers
 __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                                   int rows, int C, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float eps) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  griddep_wait();     // PDL: wait for the producers of our inputs
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -275,6 +442,106 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_kernel(const __half* 
   }
 }
 
+
+// LayerNorm, sub-warp-per-row schedule: LPR lanes share one row, each lane owns VPL 16-byte vectors of it (C = 8*VPL*LPR)
+// and keeps their gamma / beta in registers; a warp normalises 32/LPR rows per pass and two passes are in flight, the
+// warps walk the rows grid-stride.  (C = 320 / 640 / 1280 -> LPR = 8 / 16 / 32 with VPL = 5; C = 2048 -> VPL = 8.)
+template <int VPL, int LPR>
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                                       int rows, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, float eps) {
+  griddep_launch();
+  constexpr int RPW = 32 / LPR;
+  constexpr int VC = VPL * LPR;
+  constexpr int U = 2;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, j = lane % LPR;
+  float g[VPL][8], b[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c0 = (j + i * LPR) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+    b[i][0] = b0.x; b[i][1] = b0.y; b[i][2] = b0.z; b[i][3] = b0.w; b[i][4] = b1.x; b[i][5] = b1.y; b[i][6] = b1.z; b[i][7] = b1.w;
+  }
+  griddep_wait();
+  const float inv_c = 1.0f / static_cast<float>(VC * 8);
+  const int stride = gridDim.x * kLnWarps * RPW * U;
+  for (int row0 = (blockIdx.x * kLnWarps + warp) * RPW * U; row0 < rows; row0 += stride) {
+    uint4 v[U][VPL];
+    int row[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      row[u] = row0 + u * RPW + sub;
+      const uint4* xr = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(min(row[u], rows - 1)) * VC + j;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) v[u][i] = __ldg(xr + i * LPR);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s = 0.0f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h[k]);
+          s += f.x + f.y;
+        }
+      }
+#pragma unroll
+      for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      float q = 0.0f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h[k]);
+          const float dx = f.x - mean, dy = f.y - mean;
+          q = fmaf(dx, dx, q);
+          q = fmaf(dy, dy, q);
+        }
+      }
+#pragma unroll
+      for (int o = LPR >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * inv_c + eps);
+      if (row[u] < rows) {
+        uint4* yr = reinterpret_cast<uint4*>(y) + static_cast<size_t>(row[u]) * VC + j;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
+          float o8[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(h[k]);
+            o8[2 * k] = fmaf((f.x - mean) * rstd, g[i][2 * k], b[i][2 * k]);
+            o8[2 * k + 1] = fmaf((f.y - mean) * rstd, g[i][2 * k + 1], b[i][2 * k + 1]);
+          }
+          uint4 ov;
+          ov.x = pack_half2(o8[0], o8[1]);
+          ov.y = pack_half2(o8[2], o8[3]);
+          ov.z = pack_half2(o8[4], o8[5]);
+          ov.w = pack_half2(o8[6], o8[7]);
+          yr[i * LPR] = ov;
+        }
+      }
+    }
+  }
+}
+
+template <int VPL, int LPR>
+void launch_ln_rows(const void* x, void* y, int rows, const float* gamma, const float* beta, float eps, cudaStream_t st) {
+  constexpr int RPW = 32 / LPR;
+  const int need = (rows + kLnWarps * RPW * 2 - 1) / (kLnWarps * RPW * 2);
+  const int cap = udt_host::num_sms() * 3;
+  udt_host::launch_pdl(layernorm_rows_kernel<VPL, LPR>, dim3(need < cap ? need : cap), dim3(kLnWarps * 32), 0, st,
+                       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), rows, gamma, beta, eps);
+}
+
 }  // namespace
 
 extern "C" int64_t udt_groupnorm_ws_bytes(int32_t NB, int32_t HW, int32_t C, int32_t groups) {
@@ -312,6 +579,41 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
   a.groups = groups;
   a.silu = silu;
   a.eps = eps;
+  static const bool onepass_ok = [] {
+    const char* e = getenv("UDT_GN_ONEPASS");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const int S = onepass_ok ? gn_onepass_cluster(NB, HW, C) : 0;
+  if (S > 0) {
+    static bool attr1_set = false;
+    if (!attr1_set) {
+      cudaError_t e = cudaFuncSetAttribute(gn_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(gn one-pass smem): %s", cudaGetErrorString(e));
+      attr1_set = true;
+    }
+    a.rows_per_cta = (HW + S - 1) / S;
+    a.chunks = S;
+    const int rpi1 = kGn1Threads / (C / 8);
+    const size_t smem1 = static_cast<size_t>(a.rows_per_cta) * C * 2 + static_cast<size_t>(2) * rpi1 * C * sizeof(float);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(S, NB, 1);
+    cfg.blockDim = dim3(kGn1Threads, 1, 1);
+    cfg.dynamicSmemBytes = smem1;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = S;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    int na = 1;
+    na += pdl_attr(&attrs[na]);
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_onepass_kernel, a);
+    if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "udt_groupnorm_nhwc (one pass): %s", cudaGetErrorString(e));
+    return UDT_OK;
+  }
   a.rows_per_cta = gn_rows_per_cta(C, HW);
   a.chunks = (HW + a.rows_per_cta - 1) / a.rows_per_cta;
   const int VC = C / 8;
@@ -323,8 +625,8 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
     attr_set = true;
   }
   dim3 grid(a.chunks, NB);
-  gn_stats_kernel<<<grid, kGnThreads, smem_stats, st>>>(a);
-  gn_apply_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), st>>>(a);
+  udt_host::launch_pdl(gn_stats_kernel, dim3(grid), dim3(kGnThreads), smem_stats, st, a);
+  udt_host::launch_pdl(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 2 * C * sizeof(float), st, a);
   return check_launch("udt_groupnorm_nhwc");
 }
 
@@ -335,8 +637,19 @@ extern "C" int udt_layernorm(const void* x, void* y, int32_t rows, int32_t C, co
   if (rc != UDT_OK) return rc;
   if (C % 8 != 0 || C > 32 * kLnMaxVec * 8 || C < 8 || rows < 1)
     return fail(UDT_ERR_SHAPE, "udt_layernorm: rows=%d C=%d unsupported (C %% 8 == 0, C <= %d)", rows, C, 32 * kLnMaxVec * 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int VC = C / 8;
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                    reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (al && (VC == 40 || VC == 80 || VC == 160 || VC == 256)) {
+    if (VC == 40) launch_ln_rows<5, 8>(x, y, rows, gamma, beta, eps, st);
+    else if (VC == 80) launch_ln_rows<5, 16>(x, y, rows, gamma, beta, eps, st);
+    else if (VC == 160) launch_ln_rows<5, 32>(x, y, rows, gamma, beta, eps, st);
+    else launch_ln_rows<8, 32>(x, y, rows, gamma, beta, eps, st);
+    return check_launch("udt_layernorm");
+  }
   const int grid = (rows + kLnWarps - 1) / kLnWarps;
-  layernorm_kernel<<<grid, kLnWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  udt_host::launch_pdl(layernorm_kernel, dim3(grid), dim3(kLnWarps * 32), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), rows, C, gamma, beta, eps);
   return check_launch("udt_layernorm");
 }
