@@ -67,6 +67,8 @@ def main():
         ws = torch.empty(ops.groupnorm_ws_bytes(nb, hw, c) // 8, device=dev, dtype=torch.float64)
         ms = timeit(lambda: ops.groupnorm(x, g, b, 1e-5, True, out=y, ws=ws))
         out.append({"op": "groupnorm_silu", "nb": nb, "hw": hw, "c": c, "ms": round(ms, 4), "gbs": round(4.0 * x.numel() / ms / 1e6, 1)})
+        if c > 2048:
+            continue
         ms = timeit(lambda: ops.layernorm(x, g, b, 1e-5, out=y))
         out.append({"op": "layernorm", "rows": nb * hw, "c": c, "ms": round(ms, 4), "gbs": round(4.0 * x.numel() / ms / 1e6, 1)})
     for r in out:

@@ -2,15 +2,19 @@
 //
 // One CTA owns two 128-row query tiles of one (batch, head) and streams the keys/values in 128-row tiles:
 //   warp 9      TMA producer : Q tiles once, then a 3-stage ring of K / V tiles (128B-swizzled boxes)
-//   warp 8      MMA issuer   : S_t = Q_t K_j^T   (M128 N128 K64, K-major operands)      -> TMEM S_t
-//                              O_t += P_t V_j    (M128 N64 K128, V as MN-major operand) -> TMEM O_t (accumulating)
-//                              issue order per key tile j and query tile t:  S_t(j+1) before P_t V_j, so the next
-//                              scores are ready while the softmax warps still work on the other query tile.
+//   warp 8      MMA issuer   : S = Q_t K_j^T     (M128 N128 K64, K-major operands)       -> one of THREE S buffers in TMEM
+//                              O_t += P_t V_j    (M128 N64 K128, V as MN-major operand)  -> TMEM O_t (accumulating)
+//                              The score tiles of both query tiles rotate through three TMEM buffers, so the scores a
+//                              softmax warpgroup needs next are computed while it still works on its current tile
+//                              (with one buffer per query tile the exp pipe idled during every S MMA).
 //   warps 0-3 / 4-7          : softmax warpgroup of tile 0 / tile 1; thread = query row.  Online softmax in fp32
 //                              (exp2 domain) with LAZY rescaling: the running output stays in TMEM and is only
 //                              rescaled (tcgen05.ld / st round trip) when the row maximum grows by more than 2^8
 //                              over the reference maximum — the probabilities are then bounded by 256, safe in
-//                              fp16, and the final division by the row sum uses the same reference.
+//                              fp16, and the final division by the row sum uses the same reference.  After the first
+//                              key tile the scores are read from TMEM ONCE: exponentials are taken against the current
+//                              reference while the tile maximum is tracked, and only a (rare) violation of the 2^8
+//                              bound replays the tile.  The tcgen05.ld of the next 32 columns flies during the math.
 //                              P_t is written as fp16 into 128B-swizzled shared memory for the PV MMA.
 // Replaces xformers.ops.memory_efficient_attention at reference sgm/modules/attention.py:246-248.
 #include "udt_common.cuh"
@@ -25,10 +29,11 @@ constexpr int kD = 64;
 constexpr int kTileBytes = kTile * kD * 2;  // 16 KB: Q tile, K tile, V tile
 constexpr int kPBytes = kTile * kTile * 2;  // 32 KB per query tile
 constexpr int kKvStages = 3;
+constexpr int kSBufs = 3;
 constexpr int kThreads = 320;
 constexpr int kTmemCols = 512;
-constexpr int kColS = 0;    // S_t at columns [t*128, t*128+128)
-constexpr int kColO = 256;  // O_t at columns [256 + t*64, ...+64)
+constexpr int kColS = 0;    // S buffer b at columns [b*128, b*128+128)
+constexpr int kColO = 384;  // O_t at columns [384 + t*64, ...+64)
 constexpr float kLazyThreshold = 8.0f;  // log2 units
 
 struct FmhaParams {
@@ -46,9 +51,23 @@ constexpr int kOffV = kOffK + kKvStages * kTileBytes;
 constexpr int kOffP = kOffV + kKvStages * kTileBytes;
 constexpr int kSmemBytes = kOffP + 2 * kPBytes + 1024;
 
+// cursor over the score computations c = j * ntiles + t (key tile j, query tile t) without integer divisions
+struct CompCursor {
+  int c, j, t, stage, kvphase, b, u;   // stage = j % kKvStages, kvphase = (j / kKvStages) & 1, b = c % kSBufs, u = c / kSBufs
+  __device__ __forceinline__ void init() { c = j = t = stage = kvphase = b = u = 0; }
+  __device__ __forceinline__ void advance(int ntiles) {
+    ++c;
+    if (++b == kSBufs) { b = 0; ++u; }
+    if (++t == ntiles) {
+      t = 0;
+      ++j;
+      if (++stage == kKvStages) { stage = 0; kvphase ^= 1; }
+    }
+  }
+};
+
 __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_constant__ FmhaParams p) {
   griddep_launch();   // PDL: let the next kernel's prologue start
-  griddep_wait();     // PDL: wait for the producers of our inputs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -57,9 +76,10 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
   uint64_t* q_full = reinterpret_cast<uint64_t*>(base + kOffCtrl);
   uint64_t* kv_full = q_full + 1;            // [kKvStages]
   uint64_t* kv_empty = kv_full + kKvStages;  // [kKvStages]
-  uint64_t* s_full = kv_empty + kKvStages;   // [2]
-  uint64_t* p_full = s_full + 2;             // [2]
-  uint64_t* o_full = p_full + 2;             // [2]
+  uint64_t* s_full = kv_empty + kKvStages;   // [kSBufs]  scores of a computation are in TMEM
+  uint64_t* s_free = s_full + kSBufs;        // [kSBufs]  the consuming warpgroup has read them
+  uint64_t* p_full = s_free + kSBufs;        // [2]       P_t(j) is in shared memory
+  uint64_t* o_full = p_full + 2;             // [2]       P_t(j) V_j has been accumulated into O_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -69,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
   const int q0 = blockIdx.x * 2 * kTile;                 // first query row (within the batch) of this CTA
   const int ntiles = (p.Nq - q0 > kTile) ? 2 : 1;        // second query tile present?
   const int nkv = (p.Nkv + kTile - 1) / kTile;
+  const int ncomp = nkv * ntiles;
 
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&p.mapQ);
@@ -79,8 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSBufs; ++i) {
       mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&p_full[i], 128);
       mbar_init(&o_full[i], 1);
     }
@@ -91,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();     // PDL: q / k / v are produced by the previous kernel
 
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
@@ -99,56 +124,63 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
       mbar_expect_tx(q_full, static_cast<uint32_t>(ntiles * kTileBytes));
       for (int t = 0; t < ntiles; ++t)
         tma_load_2d(&p.mapQ, q_full, base + kOffQ + t * kTileBytes, col, b * p.Nq + q0 + t * kTile);
+      int s = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
-        const int s = j % kKvStages;
-        mbar_wait(&kv_empty[s], ((j / kKvStages) & 1) ^ 1u);
+        mbar_wait(&kv_empty[s], ph ^ 1u);
         mbar_expect_tx(&kv_full[s], 2u * kTileBytes);
         tma_load_2d(&p.mapK, &kv_full[s], base + kOffK + s * kTileBytes, col, b * p.Nkv + j * kTile);
         tma_load_2d(&p.mapV, &kv_full[s], base + kOffV + s * kTileBytes, col, b * p.Nkv + j * kTile);
+        if (++s == kKvStages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
-      const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
-      auto issue_s = [&](int t, int stage) {
-        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + t * kTileBytes);
-        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kOffK + stage * kTileBytes);
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const bool issuer = elect_one();
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
+    auto issue_s = [&](const CompCursor& k) {
+      if (k.t == 0) mbar_wait(&kv_full[k.stage], static_cast<uint32_t>(k.kvphase));
+      if (k.u > 0) mbar_wait(&s_free[k.b], static_cast<uint32_t>((k.u - 1) & 1));   // the previous user has read this buffer
+      tc_fence_after();
+      if (issuer) {
+        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + k.t * kTileBytes);
+        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kOffK + k.stage * kTileBytes);
 #pragma unroll
         for (int kk = 0; kk < kD / 16; ++kk)
-          umma_f16_ss(tmem_base + kColS + t * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
+          umma_f16_ss(tmem_base + kColS + k.b * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
                       idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&s_full[t]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+        umma_commit(&s_full[k.b]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    CompCursor ks, kp;   // score cursor runs kSBufs computations ahead of the PV cursor
+    ks.init();
+    kp.init();
+    for (int i = 0; i < kSBufs && ks.c < ncomp; ++i) {
+      issue_s(ks);
+      ks.advance(ntiles);
+    }
+    for (; kp.c < ncomp; kp.advance(ntiles)) {
+      mbar_wait(&p_full[kp.t], static_cast<uint32_t>(kp.j & 1));   // P_t(j) is in smem, S of this computation is released
       tc_fence_after();
-      for (int t = 0; t < ntiles; ++t) issue_s(t, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % kKvStages;
-        const uint32_t v_addr = base_addr + kOffV + s * kTileBytes;
-        for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(&p_full[t], j & 1);   // softmax t is done with S_t(j); P_t(j) is in smem; O_t is consistent
-          tc_fence_after();
-          if (j + 1 < nkv) {
-            const int sn = (j + 1) % kKvStages;
-            if (t == 0) {
-              mbar_wait(&kv_full[sn], ((j + 1) / kKvStages) & 1);
-              tc_fence_after();
-            }
-            issue_s(t, sn);               // next scores first: they are what the softmax warps wait for
-          }
-          const uint32_t p_addr = base_addr + kOffP + t * kPBytes;
+      if (issuer) {
+        const uint32_t v_addr = base_addr + kOffV + kp.stage * kTileBytes;
+        const uint32_t p_addr = base_addr + kOffP + kp.t * kPBytes;
 #pragma unroll
-          for (int kk = 0; kk < kTile / 16; ++kk) {
-            const uint64_t dp = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32);
-            const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
-            umma_f16_ss(tmem_base + kColO + t * 64, dp, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
-          }
-          umma_commit(&o_full[t]);
+        for (int kk = 0; kk < kTile / 16; ++kk) {
+          const uint64_t dp = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32);
+          const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
+          umma_f16_ss(tmem_base + kColO + kp.t * 64, dp, dv, idesc_o, (kp.j | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[s]);
+        umma_commit(&o_full[kp.t]);
+        if (kp.t == ntiles - 1) umma_commit(&kv_empty[kp.stage]);   // last reader of this K/V stage
+      }
+      __syncwarp();
+      if (ks.c < ncomp) {
+        issue_s(ks);
+        ks.advance(ntiles);
       }
     }
   } else {
@@ -158,101 +190,124 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;
       const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t s_addr = tmem_base + lane_base + kColS + t * 128;
       const uint32_t o_addr = tmem_base + lane_base + kColO + t * 64;
       uint8_t* sP = base + kOffP + t * kPBytes;
       const float sl2 = p.scale_log2;
       float m_ref = -INFINITY, l = 0.0f;
+      int sb = t, su = 0;   // S buffer / use count of this warpgroup's next computation (c = j * ntiles + t)
 
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&s_full[t], j & 1);
-        tc_fence_after();
-        const int key_lim = p.Nkv - j * kTile;  // keys >= key_lim of this tile are padding (only on the last tile)
-        const bool partial = key_lim < kTile;
-        // ---- pass 1: row maximum of the raw scores
-        float mx = -INFINITY;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(s_addr + hf * 64, v0);
-          tmem_ld32(s_addr + hf * 64 + 32, v1);
-          tmem_ld_wait();
-          if (!partial) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (hf * 64 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v0[i]));
-              if (hf * 64 + 32 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v1[i]));
-            }
-          }
-        }
-        const float m_tile = mx * sl2;
+      // rescale the running output (and row sum) when the reference maximum moves; O_t must be stable
+      auto rescale = [&](bool need, float m_tile, int j) {
+        const float m_new = need ? m_tile : m_ref;
+        const float alpha = need ? ex2_approx(m_ref - m_new) : 1.0f;  // m_ref = -inf on the first tile -> 0
+        l *= alpha;
         if (j > 0) {
-          mbar_wait(&o_full[t], (j - 1) & 1);  // P_t V_{j-1} done: P buffer reusable, O_t stable
+          mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));
           tc_fence_after();
-        }
-        // ---- lazy rescale: only when this row's maximum outgrew the reference by more than 2^8
-        const bool need = m_tile > m_ref + kLazyThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = need ? m_tile : m_ref;
-          const float alpha = need ? ex2_approx(m_ref - m_new) : 1.0f;  // m_ref = -inf on the first tile -> 0
-          l *= alpha;
-          if (j > 0) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t v[32];
-              tmem_ld32(o_addr + c * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st32(o_addr + c * 32, v);
-            }
-            tmem_st_wait();
-          }
-          m_ref = m_new;
-        }
-        // ---- pass 2: probabilities (bounded by 2^8), row sum, P -> swizzled smem
-        float rowsum = 0.0f;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(s_addr + hf * 64, v0);
-          tmem_ld32(s_addr + hf * 64 + 32, v1);
-          tmem_ld_wait();
-          uint8_t* prow = sP + hf * kTileBytes + row * 128;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            uint32_t pk[16];
+            uint32_t v[32];
+            tmem_ld32(o_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(o_addr + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+        m_ref = m_new;
+      };
+
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&s_full[sb], static_cast<uint32_t>(su & 1));
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_base + kColS + sb * 128;
+        const int key_lim = p.Nkv - j * kTile;  // keys >= key_lim of this tile are padding (only on the last tile)
+        const bool partial = key_lim < kTile;
+        uint32_t pk[64];                        // the tile's probabilities, fp16 pairs
+        float rowsum = 0.0f;
+        float mx = -INFINITY;
+        uint32_t v[32];
+        bool replay = (j == 0) || partial;      // first / ragged tile: maximum first, then the exponentials
+        if (!replay) {
+          // ---- single pass: exponentials against the current reference, tile maximum tracked alongside
+          tmem_ld32(s_addr, v);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            tmem_ld_wait_dep(v);
+            float s[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v[i]);
+            if (ch < 3) tmem_ld32(s_addr + (ch + 1) * 32, v);   // next 32 columns in flight during the math
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float s0 = __uint_as_float(c == 0 ? v0[i] : v1[i]);
-              const float s1 = __uint_as_float(c == 0 ? v0[i + 1] : v1[i + 1]);
-              float p0 = ex2_approx(fmaf(s0, sl2, -m_ref));
-              float p1 = ex2_approx(fmaf(s1, sl2, -m_ref));
+              mx = fmaxf(mx, fmaxf(s[i], s[i + 1]));
+              const float p0 = ex2_approx(fmaf(s[i], sl2, -m_ref));
+              const float p1 = ex2_approx(fmaf(s[i + 1], sl2, -m_ref));
+              rowsum += p0 + p1;
+              pk[ch * 16 + (i >> 1)] = pack_half2(p0, p1);
+            }
+          }
+          replay = __any_sync(0xffffffffu, mx * sl2 > m_ref + kLazyThreshold);
+        }
+        if (replay) {
+          // ---- two passes: row maximum of the raw scores, reference update (+ O rescale), exponentials
+          mx = -INFINITY;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!partial || ch * 32 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          const float m_tile = mx * sl2;
+          const bool need = m_tile > m_ref + kLazyThreshold;
+          if (__any_sync(0xffffffffu, need)) rescale(need, m_tile, j);
+          rowsum = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
               if (partial) {
-                const int k0 = hf * 64 + c * 32 + i;
+                const int k0 = ch * 32 + i;
                 if (k0 >= key_lim) p0 = 0.0f;
                 if (k0 + 1 >= key_lim) p1 = 0.0f;
               }
               rowsum += p0 + p1;
-              pk[i >> 1] = pack_half2(p0, p1);
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int c16 = c * 4 + g;  // 16-byte group within the 128-byte row of this 64-key half
-              *reinterpret_cast<uint4*>(prow + ((c16 ^ (row & 7)) << 4)) =
-                  make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+              pk[ch * 16 + (i >> 1)] = pack_half2(p0, p1);
             }
           }
         }
+        // the scores are consumed: hand the buffer back to the MMA warp
+        tc_fence_before();
+        mbar_arrive(&s_free[sb]);
         l += rowsum;
+        if (j > 0) {
+          mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));  // P_t V_{j-1} done: the P buffer is reusable
+          tc_fence_after();
+        }
+        // ---- P -> swizzled smem: two 64-key halves of 128-byte rows
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint8_t* prow = sP + hf * kTileBytes + row * 128;
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {   // 16-byte group within the 128-byte row of this 64-key half
+            const int q = hf * 32 + c16 * 4;
+            *reinterpret_cast<uint4*>(prow + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[q], pk[q + 1], pk[q + 2], pk[q + 3]);
+          }
+        }
         fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
-        tc_fence_before();         // TMEM reads of S_t / writes of O_t ordered before the arrive
+        tc_fence_before();         // TMEM reads of S / writes of O_t ordered before the arrive
         mbar_arrive(&p_full[t]);
+        sb += ntiles;
+        if (sb >= kSBufs) { sb -= kSBufs; ++su; }
       }
-      mbar_wait(&o_full[t], (nkv - 1) & 1);
+      mbar_wait(&o_full[t], static_cast<uint32_t>((nkv - 1) & 1));
       tc_fence_after();
       const int qrow = q0 + t * kTile + row;
       const float inv = 1.0f / l;
