@@ -32,7 +32,7 @@ extern "C" {
 #define UDT_ACT_GEGLU 2 /* out[:, j] = x_j * gelu_erf(gate_j); weight rows interleaved per column tile */
 #define UDT_ACT_RELU 3
 
-int udt_version(void);            /* ABI version (2) */
+int udt_version(void);            /* ABI version (3) */
 int udt_arch(void);               /* compute capability of the current device *10 (100 on B200); <0 on error */
 const char* udt_last_error(void); /* thread-local message of the last failing call */
 int udt_num_sms(void);
@@ -69,6 +69,8 @@ typedef struct {
   int32_t out_fp32;
   int32_t act;           /* UDT_ACT_* */
   int32_t bn_hint;       /* column tile, 0 = library picks */
+  void* workspace;       /* optional scratch (device, 16-byte aligned) for split-K partial tiles; NULL disables split-K */
+  int64_t workspace_bytes;
 } udt_igemm_desc;
 
 /* K2/K3 — segmented implicit GEMM on tcgen05/TMEM fed by TMA:

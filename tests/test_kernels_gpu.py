@@ -340,3 +340,146 @@ def test_vae_sample_pack_and_pointwise_affine(udt_lib):
     torch.cuda.synchronize()
     assert (out[..., :4].float().cpu() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
     assert out[..., 4:].abs().max().item() == 0.0
+
+
+# ------------------------------------------------------------------------------------------- round-1b additions
+@pytest.mark.parametrize("m,k,n,res", [(512, 11520, 1280, True), (512, 2560, 1280, False), (256, 4096, 640, True),
+                                       (384, 1024, 200, False)])
+def test_splitk_linear_matches_torch(udt_lib, m, k, n, res):
+    """small-M / long-K GEMMs take the split-K path (fp32 partial tiles in the workspace + reduce kernel): same result
+    as torch fp32 and as the un-split kernel (bn_hint disables split-K)"""
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(m + k + n)
+    x = _randn((m, k), g).half()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).half()
+    b = _randn((n,), g)
+    r = _randn((m, n), g).half() if res else None
+    ref = x.float() @ w.float().t() + b + (r.float() if res else 0.0)
+    rd = None if r is None else r.to(dev)
+    y = ops.linear(x.to(dev), w.to(dev), b.to(dev), residual=rd)
+    y_nosplit = ops.linear(x.to(dev), w.to(dev), b.to(dev), residual=rd, bn_hint=128)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 2e-3
+    assert _rel(y.cpu(), y_nosplit.cpu()) < 1e-3
+    # deterministic: fixed reduction order
+    y2 = ops.linear(x.to(dev), w.to(dev), b.to(dev), residual=rd)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)
+
+
+def test_splitk_conv_with_rowbias(udt_lib):
+    """8x8-resolution ResBlock conv at batch 8 (M = 512): per-image bias + fused 1x1 skip segment through split-K"""
+    from udifftext_b200 import ops, pack
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    nb, hw, cin, cout, cs = 8, 8, 640, 320, 192
+    x = _randn((nb, cin, hw, hw), g).half()
+    sk = _randn((nb, cs, hw, hw), g).half()
+    w = _randn((cout, cin, 3, 3), g, 1 / math.sqrt(9 * cin)).half()
+    ws = _randn((cout, cs, 1, 1), g, 1 / math.sqrt(cs)).half()
+    b = _randn((cout,), g)
+    rb = _randn((nb, cout), g)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1) + F.conv2d(sk.float(), ws.float()) + rb[:, :, None, None]
+    wp = pack.pack_conv3x3(w.float(), [ws.float()]).to(dev)
+    xh = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    skh = sk.permute(0, 2, 3, 1).contiguous().to(dev)
+    y = ops.conv3x3(xh, wp, b.to(dev), rowbias=rb.to(dev), skip_srcs=[skh])
+    torch.cuda.synchronize()
+    assert _rel(y.permute(0, 3, 1, 2).cpu(), ref) < 2e-3
+
+
+@pytest.mark.parametrize("m", [128, 129, 255, 256, 257, 385, 640])
+def test_pair_mode_ragged_rows(udt_lib, m):
+    """odd numbers of 128-row tiles leave a phantom tile in the last CTA pair; ragged M clips the stores"""
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(m)
+    k, n = 320, 320
+    x = _randn((m, k), g).half()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).half()
+    b = _randn((n,), g)
+    r = _randn((m, n), g).half()
+    guard = torch.full((m + 256, n), 7.0, dtype=torch.float16, device=dev)
+    ops.linear(x.to(dev), w.to(dev), b.to(dev), residual=r.to(dev), out=guard[:m])
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + b + r.float()
+    assert _rel(guard[:m].cpu(), ref) < 2e-3
+    assert bool((guard[m:] == 7.0).all())      # nothing written past the last row
+
+
+def test_linear_per_sample_rowbias(udt_lib):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(77)
+    nb, n_tok, k, n = 6, 64, 320, 320      # 64-token samples: one 128-row tile spans two samples
+    x = _randn((nb * n_tok, k), g).half()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).half()
+    b = _randn((n,), g)
+    rb = _randn((nb, n), g)
+    ref = x.float() @ w.float().t() + b + rb.repeat_interleave(n_tok, dim=0)
+    y = ops.linear(x.to(dev), w.to(dev), b.to(dev), rowbias=rb.to(dev))
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 2e-3
+
+
+@pytest.mark.parametrize("nb,hw,c0,c1,silu", [(8, 64, 1280, 0, True), (8, 64, 1280, 1280, True), (2, 256, 1280, 640, False),
+                                               (3, 1024, 640, 0, True), (1, 1024, 320, 320, True), (5, 100, 64, 0, True),
+                                               (2, 4096, 320, 0, True), (1, 37, 96, 32, False)])
+def test_groupnorm_schedules(udt_lib, nb, hw, c0, c1, silu):
+    """one-pass cluster schedule (small tensors, incl. ragged pixel counts and two-source concat) and the two-pass one"""
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(nb * hw + c0 + c1)
+    c = c0 + c1
+    x = (_randn((nb, hw, c), g) * 1.7 + 0.3).half()
+    gamma = _randn((c,), g) * 0.2 + 1.0
+    beta = _randn((c,), g) * 0.1
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    x0 = x[..., :c0].contiguous().to(dev)
+    x1 = x[..., c0:].contiguous().to(dev) if c1 else None
+    y = ops.groupnorm(x0, gamma.to(dev), beta.to(dev), 1e-5, silu, x1=x1)
+    y2 = ops.groupnorm(x0, gamma.to(dev), beta.to(dev), 1e-5, silu, x1=x1)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 2e-3
+    assert torch.equal(y, y2)                  # deterministic statistics
+
+
+@pytest.mark.parametrize("rows,c", [(32768, 320), (8192, 640), (2050, 1280), (24, 2048), (7, 320), (100, 128)])
+def test_layernorm_schedules(udt_lib, rows, c):
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(rows + c)
+    x = (_randn((rows, c), g) * 2.0 + 0.5).half()
+    gamma = _randn((c,), g) * 0.2 + 1.0
+    beta = _randn((c,), g) * 0.1
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    y = ops.layernorm(x.to(dev), gamma.to(dev), beta.to(dev), 1e-5)
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), ref) < 2e-3
+
+
+@pytest.mark.parametrize("b,n,heads", [(2, 4096, 5), (1, 1024, 10), (3, 256, 20), (2, 64, 20), (1, 192, 2), (1, 300, 1)])
+def test_fmha_rotating_buffers(udt_lib, b, n, heads):
+    """long sequences exercise the three-buffer score rotation, 64 / 192 / 300 keys the ragged last key tile"""
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(b * n + heads)
+    c = heads * 64
+    d = _randn((b * n, 3 * c), g).half().to(dev)
+    y = ops.fmha(d[:, :c], d[:, c:2 * c], d[:, 2 * c:], b, n, n, heads, 64 ** -0.5)
+    torch.cuda.synchronize()
+    q, k, v = (d[:, i * c:(i + 1) * c].float().view(b, n, heads, 64).transpose(1, 2) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b * n, c)
+    assert _rel(y.float(), ref) < 2e-3
+    # attention with a large score spread (forces reference-maximum updates after the first key tile)
+    d2 = d.clone()
+    d2[:, :c] *= 6.0
+    y2 = ops.fmha(d2[:, :c], d2[:, c:2 * c], d2[:, 2 * c:], b, n, n, heads, 64 ** -0.5)
+    q2 = d2[:, :c].float().view(b, n, heads, 64).transpose(1, 2)
+    ref2 = F.scaled_dot_product_attention(q2, k, v).transpose(1, 2).reshape(b * n, c)
+    torch.cuda.synchronize()
+    assert _rel(y2.float(), ref2) < 3e-3

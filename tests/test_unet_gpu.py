@@ -68,3 +68,25 @@ def test_full_unet_matches_reference_golden(udt_lib):
     y2 = net.forward(gold["x"], gold["t"], gold["ctx"])
     torch.cuda.synchronize()
     assert (y - y2).abs().max().item() < 1e-4
+
+
+def test_uc_cross_attention_shortcut_is_exact(udt_lib):
+    """zero unconditional context (force_uc_zero_embeddings=["label"]): skipping the uc half of every t_attn and adding
+    to_out.bias through the previous GEMM's per-sample bias reproduces the full computation (SURVEY §7 shortcut iii)"""
+    from udifftext_b200 import synth
+    from udifftext_b200.unet import UNetB200
+    dev = torch.device("cuda", 0)
+    net = UNetB200(_unet_sd("tiny"), dev, **synth.ARCH["tiny"]["unet"])
+    g = torch.Generator().manual_seed(3)
+    nb = 4
+    x = torch.randn((nb, 9, 16, 16), generator=g)
+    t = torch.tensor([999, 500, 999, 500])
+    ctx = torch.randn((nb, 12, synth.ARCH["tiny"]["unet"]["t_context_dim"]), generator=g)
+    ctx[: nb // 2] = 0.0
+    y_full = net.forward(x, t, ctx)
+    net.skip_uc_xattn = True
+    y_skip = net.forward(x, t, ctx)
+    torch.cuda.synchronize()
+    err = _rel(y_skip, y_full)
+    print("uc shortcut vs full rel-L2:", err)
+    assert err < 2e-3   # identical in real arithmetic; one fp16 rounding fewer on the uc residual stream

@@ -150,7 +150,7 @@ int make_tmap_nhwc_c32(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, 
 }  // namespace udt_host
 
 extern "C" {
-int udt_version(void) { return 2; }
+int udt_version(void) { return 3; }
 int udt_arch(void) { return udt_host::arch(); }
 const char* udt_last_error(void) { return udt_host::error_buffer(); }
 int udt_num_sms(void) { return udt_host::num_sms(); }

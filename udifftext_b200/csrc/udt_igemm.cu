@@ -64,6 +64,11 @@ struct IGemmParams {
   int32_t bw, bh, bn;
   int32_t tiles_w, tiles_h, tiles_nb, tiles_n, num_tiles;
   uint32_t mg_n, mg_w, mg_h;   // fast_div magic numbers of tiles_n, tiles_w, tiles_h
+  // split-K (small-M, weight-streaming problems): work item = (tile, split); split s accumulates K steps
+  // [s*kper, min(ksteps, (s+1)*kper)) and stores its fp32 partial tile at out + s*split_stride (reduced by a second kernel)
+  int32_t ksplit, kper;
+  uint32_t mg_s;
+  long long split_stride;
   int32_t N_out, BN, stages;
   const float* bias;
   const float* rowbias;
@@ -127,9 +132,28 @@ __device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int tile,
   return t;
 }
 
+struct WorkItem {
+  int tile, split, k0, k1;
+};
+__device__ __forceinline__ WorkItem decode_work(const IGemmParams& p, int w) {
+  WorkItem it;
+  if (p.ksplit > 1) {
+    it.tile = fast_div(w, p.mg_s, p.ksplit);
+    it.split = w - it.tile * p.ksplit;
+    it.k0 = it.split * p.kper;
+    it.k1 = min(p.ksteps, it.k0 + p.kper);
+  } else {
+    it.tile = w;
+    it.split = 0;
+    it.k0 = 0;
+    it.k1 = p.ksteps;
+  }
+  return it;
+}
+
 // Finish `cnt` (<= 32) consecutive output columns of one row: f[] holds the fp32 accumulators.
 __device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[32], int cnt, size_t m, int img,
-                                               int col, bool fast) {
+                                               int col, bool fast, int split) {
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -149,7 +173,12 @@ __device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
   }
   if (p.out_fp32) {
-    float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col;
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(split) * p.split_stride + m * p.ldo + col;
+    if (p.ksplit > 1 && cnt == 32 && (p.ldo & 3) == 0) {   // split-K partial tile: raw accumulators, 16-byte stores
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      return;
+    }
     if (p.residual != nullptr) {
       const __half* r = p.residual + m * p.ldr + col;
       for (int j = 0; j < cnt; ++j) f[j] += __half2float(r[j]);
@@ -272,9 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       uint32_t phase = 0;
       int iter = 0;
       const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;   // the leader's full barriers
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
-        const TileCoord tc = decode_tile<kPair>(p, tile, rank);
+      for (int wk = tile0; wk < p.num_tiles; wk += tile_step, ++iter) {
+        const WorkItem wi = decode_work(p, wk);
+        const TileCoord tc = decode_tile<kPair>(p, wi.tile, rank);
         if (issuer) trace_ev(p, iter, 0);
+        int kstep = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const CUtensorMap* ma = &p.mapA[s];
           const int taps = p.seg_taps[s];
@@ -283,7 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           for (int t = 0; t < taps; ++t) {
             const int dy = (taps == 9) ? (t / 3 - p.seg_pad[s]) : 0;
             const int dx = (taps == 9) ? (t % 3 - p.seg_pad[s]) : 0;
-            for (int c = 0; c < kc; ++c) {
+            for (int c = 0; c < kc; ++c, ++kstep) {
+              if (kstep < wi.k0 || kstep >= wi.k1) continue;   // another split's K range
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               if (issuer) {
                 if (kPair) {
@@ -314,9 +346,10 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-        const int n_row = (tile % p.tiles_n) * p.BN + rank * b_rows;
-        for (int k = 0; k < p.ksteps; ++k) {
+      for (int wk = tile0; wk < p.num_tiles; wk += tile_step) {
+        const WorkItem wi = decode_work(p, wk);
+        const int n_row = (wi.tile - fast_div(wi.tile, p.mg_n, p.tiles_n) * p.tiles_n) * p.BN + rank * b_rows;
+        for (int k = wi.k0; k < wi.k1; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (issuer) {
             if (kPair) {
@@ -347,14 +380,15 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       int as = 0;
       uint32_t aphase = 0;
       int iter = 0;
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
+      for (int wk = tile0; wk < p.num_tiles; wk += tile_step, ++iter) {
+        const WorkItem wi = decode_work(p, wk);
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
-        for (int k = 0; k < p.ksteps; ++k) {
+        for (int k = wi.k0; k < wi.k1; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (k == 0 && issuer) trace_ev(p, iter, 2);
+          if (k == wi.k0 && issuer) trace_ev(p, iter, 2);
           const uint64_t da = umma_desc_kmajor_sw128(sA_addr + stage * kABytes);
           const uint64_t db = umma_desc_kmajor_sw128(sB_addr + stage * b_bytes);
           if (issuer) {
@@ -363,10 +397,10 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
               // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
               if (kPair)
                 umma_f16_ss_pair(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                                 (k | kk) != 0 ? 1u : 0u);
+                                 (k > wi.k0 || kk != 0) ? 1u : 0u);
               else
                 umma_f16_ss(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                            (k | kk) != 0 ? 1u : 0u);
+                            (k > wi.k0 || kk != 0) ? 1u : 0u);
             }
             // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
             if (kPair) umma_commit_pair(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
@@ -651,8 +685,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
                       ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-      const TileCoord tc = decode_tile<kPair>(p, tile, rank);
+    for (int wk = tile0; wk < p.num_tiles; wk += tile_step) {
+      const WorkItem wi = decode_work(p, wk);
+      const TileCoord tc = decode_tile<kPair>(p, wi.tile, rank);
       const int w = tc.w0 + r_w, h = tc.h0 + r_h, n = tc.n0 + r_n;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.NB);
       const size_t m = (static_cast<size_t>(n) * p.H + h) * p.W + w;
@@ -708,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             const int cnt = min(32, p.N_out - col);
-            finish_columns(p, f, cnt, m, n, col, fast);
+            finish_columns(p, f, cnt, m, n, col, fast, wi.split);
           }
         }
       } else {  // BN == 16
@@ -721,7 +756,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = (j < 16) ? __uint_as_float(v[j & 15]) : 0.0f;
           const int cnt = min(16, p.N_out - col);
-          finish_columns(p, f, cnt, m, n, col, false);
+          finish_columns(p, f, cnt, m, n, col, false, wi.split);
         }
       }
       tc_fence_before();
@@ -744,6 +779,56 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     tc_fence_after();
     if (kPair) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+// split-K second kernel: out[m, n] = sum_s ws[s][m][n] + bias[n] + rowbias[img(m)][n] + residual[m][n], 8 columns per thread
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int S, long long split_stride, int M,
+                                                            int N, const float* __restrict__ bias,
+                                                            const float* __restrict__ rowbias, int ld_rowbias, int rows_per_img,
+                                                            const __half* __restrict__ residual, int ldr, __half* __restrict__ out,
+                                                            int ldo) {
+  griddep_launch();
+  griddep_wait();
+  const int nv = N >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * nv) return;
+  const int m = static_cast<int>(idx / nv);
+  const int col = static_cast<int>(idx - static_cast<long long>(m) * nv) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  const float* src = ws + static_cast<long long>(m) * N + col;
+  for (int s = 0; s < S; ++s) {       // fixed order: deterministic
+    const float4 a0 = *reinterpret_cast<const float4*>(src + s * split_stride);
+    const float4 a1 = *reinterpret_cast<const float4*>(src + s * split_stride + 4);
+    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+    acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+  }
+  if (bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(bias + col + j);
+  }
+  if (rowbias != nullptr) {
+    const float* rb = rowbias + static_cast<long long>(m / rows_per_img) * ld_rowbias + col;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __ldg(rb + j);
+  }
+  if (residual != nullptr) {
+    const uint4 rv = *reinterpret_cast<const uint4*>(residual + static_cast<long long>(m) * ldr + col);
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 rf = __half22float2(rh[j]);
+      acc[2 * j] += rf.x;
+      acc[2 * j + 1] += rf.y;
+    }
+  }
+  uint4 ov;
+  ov.x = pack_half2(acc[0], acc[1]);
+  ov.y = pack_half2(acc[2], acc[3]);
+  ov.z = pack_half2(acc[4], acc[5]);
+  ov.w = pack_half2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(out + static_cast<long long>(m) * ldo + col) = ov;
 }
 
 unsigned long long* g_trace_buf = nullptr;
@@ -879,16 +964,45 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   int BN = geglu_tile > 0 ? geglu_tile : (d->bn_hint > 0 ? d->bn_hint : pick_bn(N_out, tiles_m, ksteps_est, pair, sms));
   if (BN != 16 && (BN % 32 != 0 || BN < 32 || BN > 256)) return fail(UDT_ERR_SHAPE, "udt_igemm: BN=%d unsupported", BN);
   if (BN == 16) pair = false;
+  // split-K: a small-M problem (few tiles, long K) streams its weights with every SM by splitting the K range; the
+  // fp32 partial tiles go to the caller's workspace and a second kernel reduces them and applies the epilogue
+  int ksplit = 1, kper = ksteps_est;
+  static const int split_env = env_int("UDT_IGEMM_SPLITK", 1);
+  if (split_env != 0 && d->bn_hint == 0 && act == UDT_ACT_NONE && !d->out_fp32 && d->workspace != nullptr && N_out % 8 == 0 &&
+      N_out >= 64 && d->ldo % 8 == 0 && (d->residual == nullptr || d->ldr % 8 == 0) &&
+      ((reinterpret_cast<uintptr_t>(d->out) | reinterpret_cast<uintptr_t>(d->residual)) & 15) == 0) {
+    const int units = pair ? sms / 2 : sms;
+    const int tm = pair ? (tiles_m + 1) / 2 : tiles_m;
+    // widest column tile that wastes < 10 % of the MMA work
+    int bn_s = 256;
+    for (int cand : {256, 224, 192, 160, 128, 96, 64}) {
+      const int tn = (N_out + cand - 1) / cand;
+      if (tn * cand * 10 <= N_out * 11) { bn_s = cand; break; }
+      bn_s = cand;
+    }
+    const int tiles_s = tm * ((N_out + bn_s - 1) / bn_s);
+    int want = units / tiles_s;
+    if (want > ksteps_est / 8) want = ksteps_est / 8;
+    if (want >= 2) {
+      kper = (ksteps_est + want - 1) / want;
+      ksplit = (ksteps_est + kper - 1) / kper;
+      const long long need = static_cast<long long>(ksplit) * NB * H * W * N_out * 4;
+      if (ksplit >= 2 && need <= d->workspace_bytes) BN = bn_s; else ksplit = 1;
+    }
+  }
   p.BN = BN;
   p.N_out = N_out;
   p.tiles_n = (N_out + BN - 1) / BN;
-  p.num_tiles = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n;
+  p.ksplit = ksplit;
+  p.kper = ksplit > 1 ? kper : ksteps_est;
+  p.num_tiles = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n * ksplit;
   const int b_rows = pair ? BN / 2 : BN;
   {
     auto magic = [](int dv) { return dv <= 1 ? 0u : static_cast<uint32_t>(((1ull << 32) + dv - 1) / dv); };
     p.mg_n = magic(p.tiles_n);
     p.mg_w = magic(p.tiles_w);
     p.mg_h = magic(p.tiles_h);
+    p.mg_s = magic(p.ksplit);
     const unsigned long long worst = static_cast<unsigned long long>(2 * p.num_tiles + 2) *
         static_cast<unsigned long long>(p.tiles_n > p.tiles_w ? (p.tiles_n > p.tiles_h ? p.tiles_n : p.tiles_h)
                                                               : (p.tiles_w > p.tiles_h ? p.tiles_w : p.tiles_h));
@@ -927,7 +1041,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && (d->ldo % 8 == 0) &&
                          (d->residual == nullptr || (((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && d->ldr % 8 == 0));
   const int n_logical = act == UDT_ACT_GEGLU ? N_out / 2 : N_out;
-  p.staged = (!d->out_fp32 && BN >= 32 && aligned16 && n_logical >= 8) ? 1 : 0;
+  p.staged = (ksplit == 1 && !d->out_fp32 && BN >= 32 && aligned16 && n_logical >= 8) ? 1 : 0;
   int epi_bytes = 0;
   if (p.staged) {
     // every epilogue warp stores its own 32-row slab of the tile: a {sbw, sbh, sbn} pixel box
@@ -971,6 +1085,16 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   p.ldo = d->ldo;
   p.out_fp32 = d->out_fp32;
   p.act = act;
+  const long long M_rows = static_cast<long long>(NB) * H * W;
+  if (ksplit > 1) {   // the GEMM kernel writes raw fp32 partial tiles; bias / per-image bias / residual move to the reduce kernel
+    p.out = d->workspace;
+    p.ldo = N_out;
+    p.out_fp32 = 1;
+    p.split_stride = M_rows * N_out;
+    p.bias = nullptr;
+    p.rowbias = nullptr;
+    p.residual = nullptr;
+  }
 
   static int dbg = -1;
   if (dbg < 0) {
@@ -995,13 +1119,20 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
     else mode = 0;
   }
   switch (mode * 2 + (pair ? 1 : 0)) {
-    case 0: return launch_igemm<false, 0>(p, grid, smem, st);
-    case 1: return launch_igemm<true, 0>(p, grid, smem, st);
-    case 2: return launch_igemm<false, 1>(p, grid, smem, st);
-    case 3: return launch_igemm<true, 1>(p, grid, smem, st);
-    case 4: return launch_igemm<false, 2>(p, grid, smem, st);
-    case 5: return launch_igemm<true, 2>(p, grid, smem, st);
-    case 6: return launch_igemm<false, 3>(p, grid, smem, st);
-    default: return launch_igemm<true, 3>(p, grid, smem, st);
+    case 0: rc = launch_igemm<false, 0>(p, grid, smem, st); break;
+    case 1: rc = launch_igemm<true, 0>(p, grid, smem, st); break;
+    case 2: rc = launch_igemm<false, 1>(p, grid, smem, st); break;
+    case 3: rc = launch_igemm<true, 1>(p, grid, smem, st); break;
+    case 4: rc = launch_igemm<false, 2>(p, grid, smem, st); break;
+    case 5: rc = launch_igemm<true, 2>(p, grid, smem, st); break;
+    case 6: rc = launch_igemm<false, 3>(p, grid, smem, st); break;
+    default: rc = launch_igemm<true, 3>(p, grid, smem, st); break;
   }
+  if (rc != UDT_OK || ksplit == 1) return rc;
+  const long long work = M_rows * (N_out / 8);
+  launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>((work + 255) / 256)), dim3(256), 0, st,
+             reinterpret_cast<const float*>(d->workspace), ksplit, p.split_stride, static_cast<int>(M_rows), N_out, d->bias,
+             d->rowbias, d->ld_rowbias, H * W, reinterpret_cast<const __half*>(d->residual), d->ldr,
+             reinterpret_cast<__half*>(d->out), d->ldo);
+  return check_launch("udt_igemm (split-K reduce)");
 }

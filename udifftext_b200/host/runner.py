@@ -41,6 +41,7 @@ class StepRunner:
         self.table: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
+        self.skip_uc = False       # this request's unconditional context is all zeros (UNetB200.skip_uc_xattn)
 
     # ------------------------------------------------------------------------------------------ per request
     def begin(self, x: torch.Tensor, cond: Dict, uc: Dict, denoiser: DiscreteDenoiser, sigmas: torch.Tensor,
@@ -52,6 +53,11 @@ class StepRunner:
         self.cat_c.copy_(cond["concat"])
         ctx = torch.cat([uc["t_crossattn"], cond["t_crossattn"]], dim=0)      # uc half first (guiders.py:36)
         u.context_kv(ctx, out=self.kv)
+        # exact shortcut for a zero unconditional context (one host read per request, outside the step loop)
+        skip = bool((uc["t_crossattn"] == 0).all().item())
+        if skip != self.skip_uc:
+            self.skip_uc = skip
+            self.graph = None          # the captured step depends on the flag
         k = step_constants(denoiser, sigmas, s_churn, s_tmin, s_tmax)
         if float(k["gamma"].abs().max()) != 0.0:
             raise NotImplementedError("s_churn > 0 (stochastic sampling) is not used by UDiffText (util.py:39)")
@@ -70,6 +76,7 @@ class StepRunner:
         ops.cfg_pack(self.x, self.cat_uc, self.cat_c, self.row[0, ew: ew + 1], self.unet_in)
         prev = u.export_attn_maps
         u.export_attn_maps = export
+        u.skip_uc_xattn = self.skip_uc
         try:
             u.forward_nhwc(self.unet_in, self.row[:, :ew].expand(2 * self.B, ew), self.kv, self.ctx_len, out=self.eps)
         finally:

@@ -91,6 +91,19 @@ def profile_step(runner, warm: int = 2, reps: int = 3) -> dict:
     return {"by_op": acc, "step_ms_eager_sum": total, "step_ms_graph": step_ms_graph}
 
 
+_SPLITK_WS = {}   # device index -> fp32 scratch for split-K partial tiles (stream ordered, shared by all calls)
+SPLITK_WS_BYTES = 64 << 20
+
+
+def _splitk_ws(device: torch.device) -> torch.Tensor:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = torch.empty(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32)
+        _SPLITK_WS[key] = ws
+    return ws
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -134,6 +147,8 @@ def igemm(
     d.ld_rowbias = 0 if rowbias is None else (n_out if ld_rowbias is None else ld_rowbias)
     d.residual, d.ldr = _ptr(residual), ldr
     d.out, d.ldo, d.out_fp32, d.act, d.bn_hint = out.data_ptr(), ldo, int(out_fp32), act, bn_hint
+    ws = _splitk_ws(out.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     if SHAPE_LOG is not None:
         k = sum(src[3] * ((src[1] + 63) // 64 * 64) for src in srcs)
         tag = "+".join(f"{src[3]}x{src[1]}" + (f"s{src[4]}" if len(src) > 4 and src[4] != 1 else "") for src in srcs)
@@ -145,9 +160,10 @@ def igemm(
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, act: int = UDT_ACT_NONE,
-           out_fp32: bool = False, bn_hint: int = 0) -> torch.Tensor:
+           out_fp32: bool = False, bn_hint: int = 0, rowbias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y[M, N] = act(x[M, K] @ weight[N, K]^T + bias) (+ residual); fp16 in, fp16 (or fp32) out.  `x` and `weight`
-    may be row-strided 2-D views (unit column stride)."""
+    may be row-strided 2-D views (unit column stride).  `rowbias` fp32 [G, N] adds row g to the g-th block of M / G
+    consecutive rows (a per-sample bias)."""
     m, k = x.shape
     n = weight.shape[0]
     n_log = n // 2 if act == UDT_ACT_GEGLU else n
@@ -156,8 +172,11 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         bn_hint = GEGLU_TILE          # the column interleave the weight was packed with
     if out is None:
         out = torch.empty((m, n_log), device=x.device, dtype=torch.float32 if out_fp32 else torch.float16)
-    return igemm([(x, k, x.stride(0), 1)], 1, 1, m, weight, n, out, out.stride(0), bias=bias, residual=residual,
-                 ldr=0 if residual is None else residual.stride(0), out_fp32=out_fp32, act=act, bn_hint=bn_hint)
+    g = 1 if rowbias is None else rowbias.shape[0]
+    assert m % g == 0
+    return igemm([(x, k, x.stride(0), 1)], g, 1, m // g, weight, n, out, out.stride(0), bias=bias, residual=residual,
+                 ldr=0 if residual is None else residual.stride(0), out_fp32=out_fp32, act=act, bn_hint=bn_hint,
+                 rowbias=rowbias, ld_rowbias=None if rowbias is None else rowbias.stride(0))
 
 
 def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
