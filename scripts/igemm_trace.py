@@ -15,6 +15,7 @@ def run(fn, label, flops, iters=20):
     dev = torch.device("cuda", 0)
     L = lib.load()
     stride = L.udt_debug_set_trace(None, 0)
+    assert stride > 0, "tracing is compiled out: rebuild with `UDT_TRACE=1 python -m udifftext_b200.build --force`"
     # timing without trace
     for _ in range(3):
         fn()

@@ -33,6 +33,12 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC or add /usr/local/cuda/bin to PATH)")
 
 
+def _flags() -> list:
+    """UDT_TRACE=1 compiles the role-timeline trace and the UDT_IGEMM_DEBUG experiment switches into udt_igemm
+    (scripts/igemm_trace.py); production builds leave them out of the hot loops."""
+    return NVCC_FLAGS + (["-DUDT_IGEMM_TRACE"] if os.environ.get("UDT_TRACE", "0") not in ("", "0") else [])
+
+
 def _source_digest() -> str:
     h = hashlib.sha256()
     names = sorted(os.listdir(CSRC)) + ["../../include/udt_api.h"]
@@ -42,7 +48,7 @@ def _source_digest() -> str:
             h.update(name.encode())
             with open(path, "rb") as f:
                 h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -54,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if f.read().strip() == digest:
                 return LIB_PATH
     os.makedirs(os.path.dirname(STAMP_PATH), exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *_flags(), "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(os.path.dirname(STAMP_PATH), "nvcc.log"), "w") as f:

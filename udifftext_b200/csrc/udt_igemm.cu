@@ -97,8 +97,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef UDT_IGEMM_TRACE
+constexpr bool kTraceBuild = true;    // role timestamps + UDT_IGEMM_DEBUG experiment switches compiled in (tuning builds)
+#else
+constexpr bool kTraceBuild = false;   // production: no trace / debug code in the hot loops
+#endif
+#define UDT_DBG(p, bit) (kTraceBuild && ((p).debug & (bit)))
+
 __device__ __forceinline__ void trace_ev(const IGemmParams& p, int iter, int ev, bool fine = false) {
-  if (p.trace != nullptr && iter < kTraceTiles && (((p.debug & 16) != 0) == fine || ev == 4))
+  if (kTraceBuild && p.trace != nullptr && iter < kTraceTiles && (((p.debug & 16) != 0) == fine || ev == 4))
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 4 + iter * kTraceEvents + ev] =
         static_cast<unsigned long long>(clock64());
 }
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();     // PDL: everything above overlapped the previous kernel; its results are needed from here on
-  if (p.trace != nullptr && threadIdx.x == 0) {
+  if (kTraceBuild && p.trace != nullptr && threadIdx.x == 0) {
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 0] = globaltimer_ns();
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 2] = static_cast<unsigned long long>(clock64());
   }
@@ -552,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
       if (!has_work) release_acc(as);              // nothing to read: release our share of the accumulator buffer
       uint32_t v[32];
-      if (has_work && !geglu && !(p.debug & 8)) tmem_ld32(taddr + first_c * kChunkCols, v);   // prologue of the load pipeline
+      if (has_work && !geglu && !UDT_DBG(p, 8)) tmem_ld32(taddr + first_c * kChunkCols, v);   // prologue of the load pipeline
       for (int c = first_c; has_work && c < nchunks; c += estep) {
         const int b = ob;
         if (++ob == p.out_bufs) ob = 0;
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             f[j] = x * gelu_erf_f(gt);
           }
         } else {
-          if (!(p.debug & 8)) tmem_ld_wait_dep(v);   // this chunk's accumulators have landed in v[]
+          if (!UDT_DBG(p, 8)) tmem_ld_wait_dep(v);   // this chunk's accumulators have landed in v[]
           if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 0, true);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -580,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
             f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
-          if (c + estep < nchunks && !(p.debug & 8)) tmem_ld32(taddr + (c + estep) * kChunkCols, v);   // next chunk's load in flight
+          if (c + estep < nchunks && !UDT_DBG(p, 8)) tmem_ld32(taddr + (c + estep) * kChunkCols, v);   // next chunk's load in flight
           if constexpr (kGeneral) {
             if (!bias_staged_rb) {
               const float* rb = p.rowbias + static_cast<size_t>(my_img) * p.ld_rowbias + col_tile + c0;
@@ -620,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
         }
         if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 1, true);
         // the slab store that last used sOut[b] (out_bufs chunks ago) must have finished reading it
-        if (issuer && !(p.debug & 32)) {
+        if (issuer && !UDT_DBG(p, 32)) {
           if (p.out_bufs == 4) tma_store_wait_read<3>();
           else if (p.out_bufs == 3) tma_store_wait_read<2>();
           else tma_store_wait_read<1>();
@@ -628,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
         __syncwarp();
         if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 2, true);
         uint8_t* orow = my_out_row0 + b * kSlabBytes;
-        if (!(p.debug & 4))
+        if (!UDT_DBG(p, 4))
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 ov;
@@ -638,14 +645,14 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           ov.w = pack_half2(f[q * 8 + 6], f[q * 8 + 7]);
           *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(q) ^ swz) << 4)) = ov;
         }
-        if (!(p.debug & 2)) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA engine
+        if (!UDT_DBG(p, 2)) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();                              // slab complete in sOut[b]; the residual slab is consumed
         if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 3, true);
         if (issuer) {
           const int col = col_tile + c0;
-          if (col < n_logical && !(p.debug & 1))
+          if (col < n_logical && !UDT_DBG(p, 1))
             tma_store_4d(&p.mapOut, sOut + b * kSlabBytes, col, tc.w0 + wq, tc.h0 + hq, tc.n0 + nq);
-          if (!(p.debug & 64)) tma_store_commit();
+          if (!UDT_DBG(p, 64)) tma_store_commit();
           if (has_res_stage) prefetch_residual();  // refill the residual slab just consumed
         }
         if (tracer && eg == 0 && c == first_c) trace_ev(p, iter, 6, true);
@@ -771,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
 
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();   // the peer may still read our operands / signal our barriers
-  if (p.trace != nullptr && threadIdx.x == 0) {
+  if (kTraceBuild && p.trace != nullptr && threadIdx.x == 0) {
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 1] = globaltimer_ns();
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 3] = static_cast<unsigned long long>(clock64());
   }
@@ -903,6 +910,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 extern "C" int udt_debug_set_trace(void* buf, int64_t nbytes) {
+  if (!kTraceBuild) return 0;   // production build: tracing is compiled out (rebuild with UDT_TRACE=1)
   g_trace_buf = reinterpret_cast<unsigned long long*>(buf);
   g_trace_bytes = nbytes;
   return kTraceStride;
@@ -983,7 +991,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
     const int tiles_s = tm * ((N_out + bn_s - 1) / bn_s);
     int want = units / tiles_s;
     if (want > ksteps_est / 8) want = ksteps_est / 8;
-    if (want >= 2) {
+    if (want >= 2 && ksteps_est >= 64) {   // short K: the second kernel costs more than the idle SMs
       kper = (ksteps_est + want - 1) / want;
       ksplit = (ksteps_est + kper - 1) / kper;
       const long long need = static_cast<long long>(ksplit) * NB * H * W * N_out * 4;

@@ -17,6 +17,7 @@ from .lib import UDT_ACT_GEGLU, UDT_ACT_NONE, UDT_ACT_RELU, UDT_ACT_SILU, GemmSr
 _launches = 0   # C-ABI compute calls issued by this process (each is one or two kernel launches of libudt_b200)
 SHAPE_LOG = None  # when a list: one problem-shape tuple per call (scripts/profile_unet_step.py)
 _prof = None    # when a list: (entry point, start event, end event) per call — see profile_step()
+CALL_LOG = None  # when a list: (entry point, bound function, args, shape) per call, for scripts/profile_step_graph.py
 
 
 def launch_count() -> int:
@@ -34,6 +35,8 @@ def _invoke(name: str, *args, shape=None) -> None:
         SHAPE_LOG.append(shape if shape is not None else tuple(a for a in args if isinstance(a, int) and a < (1 << 24)))
     fn = getattr(_lib.load(), name)
     _launches += 1
+    if CALL_LOG is not None:
+        CALL_LOG.append((name, fn, args, shape if shape is not None else tuple(a for a in args if isinstance(a, int) and a < (1 << 24))))
     if _prof is None:
         rc = fn(*args, _stream())
     else:
