@@ -77,38 +77,42 @@ __device__ __forceinline__ void gn_group_fold(const float* ps, const float* pq, 
   }
 }
 
-// pass 1: deterministic per-CTA partial statistics (no atomics anywhere)
+// pass 1: deterministic per-CTA partial statistics (no atomics anywhere).  The CTA's slab of pixels is fetched with
+// bulk asynchronous copies (the whole slab in flight at once, one round trip) and summed out of shared memory.
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
   griddep_launch();   // PDL: let the next kernel's prologue start
-  griddep_wait();     // PDL: wait for the producers of our inputs
-  extern __shared__ float sm[];  // [rpi][C] sums, then [rpi][C] sums of squares
+  extern __shared__ __align__(16) uint8_t gsm2[];
+  __shared__ uint64_t s_bar;
   const int n = blockIdx.y;
   const int row0 = blockIdx.x * a.rows_per_cta;
-  const int row1 = min(a.HW, row0 + a.rows_per_cta);
+  const int nrows = min(a.HW, row0 + a.rows_per_cta) - row0;
   const int VC = a.C / 8;
   const int vcols = min(VC, static_cast<int>(blockDim.x));
   const int rpi = max(1, static_cast<int>(blockDim.x) / VC);
-  float* s_sum = sm;
-  float* s_sq = sm + rpi * a.C;
+  const uint4* slab = reinterpret_cast<const uint4*>(gsm2);
+  float* s_sum = reinterpret_cast<float*>(gsm2 + static_cast<size_t>(a.rows_per_cta) * a.C * 2);
+  float* s_sq = s_sum + rpi * a.C;
+  const size_t pix0 = static_cast<size_t>(n) * a.HW + row0;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  griddep_wait();     // PDL: wait for the producers of our inputs
+  if (threadIdx.x == 0) mbar_expect_tx(&s_bar, static_cast<uint32_t>(nrows) * static_cast<uint32_t>(a.C) * 2u);
+  for (int row = threadIdx.x; row < nrows; row += blockDim.x) {
+    uint8_t* dst = gsm2 + static_cast<size_t>(row) * a.C * 2;
+    bulk_load_1d(dst, a.x0 + (pix0 + row) * a.C0, static_cast<uint32_t>(a.C0) * 2u, &s_bar);
+    if (a.C1 > 0) bulk_load_1d(dst + a.C0 * 2, a.x1 + (pix0 + row) * a.C1, static_cast<uint32_t>(a.C1) * 2u, &s_bar);
+  }
+  mbar_wait(&s_bar, 0);
   const int r = threadIdx.x / vcols;
   if (r < rpi) {
-    const size_t pix0 = static_cast<size_t>(n) * a.HW;
     for (int vc = threadIdx.x % vcols; vc < VC; vc += vcols) {
       float s[8], q[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0f;
-      int row = row0 + r;
-      for (; row + 3 * rpi < row1; row += 4 * rpi) {  // 4 independent 16-byte loads in flight
-        const uint4 v0 = gn_load_vec(a, pix0 + row, vc);
-        const uint4 v1 = gn_load_vec(a, pix0 + row + rpi, vc);
-        const uint4 v2 = gn_load_vec(a, pix0 + row + 2 * rpi, vc);
-        const uint4 v3 = gn_load_vec(a, pix0 + row + 3 * rpi, vc);
-        gn_accum(v0, s, q);
-        gn_accum(v1, s, q);
-        gn_accum(v2, s, q);
-        gn_accum(v3, s, q);
-      }
-      for (; row < row1; row += rpi) gn_accum(gn_load_vec(a, pix0 + row, vc), s, q);
+      for (int row = r; row < nrows; row += rpi) gn_accum(slab[row * VC + vc], s, q);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s_sum[r * a.C + vc * 8 + j] = s[j];
@@ -130,18 +134,16 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
   }
 }
 
-// pass 2: fold the partials in a fixed order, then y = x * A[c] + B[c] (+SiLU) with per-channel A/B in smem
+// pass 2: fold the partials in a fixed order, then y = x * A[c] + B[c] (+SiLU); every thread owns fixed 8-channel
+// vectors (its A / B coefficients live in registers) and walks the CTA's rows with 4 loads in flight
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
   griddep_launch();   // PDL: let the next kernel's prologue start
-  griddep_wait();     // PDL: wait for the producers of our inputs
-  extern __shared__ float sm[];  // A[C], B[C]
   __shared__ double s_red[kGnMaxGroups][8][2];
   __shared__ float s_mean[kGnMaxGroups];
   __shared__ float s_rstd[kGnMaxGroups];
-  float* sA = sm;
-  float* sB = sm + a.C;
   const int n = blockIdx.y;
   const int cpg = a.C / a.groups;
+  griddep_wait();     // PDL: wait for the producers of our inputs
   {
     const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
     if (g < a.groups) {
@@ -171,69 +173,57 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float A = s_rstd[g] * __ldg(a.gamma + c);
-    sA[c] = A;
-    sB[c] = __ldg(a.beta + c) - s_mean[g] * A;
-  }
-  __syncthreads();
   const int VC = a.C / 8;
+  const int vcols = min(VC, static_cast<int>(blockDim.x));
+  const int rpi = max(1, static_cast<int>(blockDim.x) / VC);
+  const int r = threadIdx.x / vcols;
+  if (r >= rpi) return;
   const int row0 = blockIdx.x * a.rows_per_cta;
-  const int row1 = min(a.HW, row0 + a.rows_per_cta);
-  const int total = (row1 - row0) * VC;
+  const int nrows = min(a.HW, row0 + a.rows_per_cta) - row0;
   const size_t pix0 = static_cast<size_t>(n) * a.HW + row0;
-  constexpr int U = 4;
-  for (int i0 = threadIdx.x; i0 < total; i0 += U * kGnThreads) {
-    uint4 v[U];
-    int vcs[U];
-    size_t pix[U];
+  for (int vc = threadIdx.x % vcols; vc < VC; vc += vcols) {
+    float A[8], B[8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kGnThreads;
-      if (i < total) {
-        const int row = i / VC;
-        vcs[u] = i - row * VC;
-        pix[u] = pix0 + row;
-        v[u] = gn_load_vec(a, pix[u], vcs[u]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int c = vc * 8 + j;
+      const int g = c / cpg;
+      A[j] = s_rstd[g] * __ldg(a.gamma + c);
+      B[j] = __ldg(a.beta + c) - s_mean[g] * A[j];
     }
+    auto finish = [&](const uint4& v, size_t pix) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      float o[8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kGnThreads;
-      if (i < total) {
-        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
-        const int c0 = vcs[u] * 8;
-        const float4 A0 = *reinterpret_cast<const float4*>(sA + c0);
-        const float4 A1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
-        const float4 B0 = *reinterpret_cast<const float4*>(sB + c0);
-        const float4 B1 = *reinterpret_cast<const float4*>(sB + c0 + 4);
-        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-        const float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-        float o[8];
-        o[0] = fmaf(f0.x, A0.x, B0.x);
-        o[1] = fmaf(f0.y, A0.y, B0.y);
-        o[2] = fmaf(f1.x, A0.z, B0.z);
-        o[3] = fmaf(f1.y, A0.w, B0.w);
-        o[4] = fmaf(f2.x, A1.x, B1.x);
-        o[5] = fmaf(f2.y, A1.y, B1.y);
-        o[6] = fmaf(f3.x, A1.z, B1.z);
-        o[7] = fmaf(f3.y, A1.w, B1.w);
-        if (a.silu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = silu_tanh(o[j]);
-        }
-        uint4 ov;
-        ov.x = pack_half2(o[0], o[1]);
-        ov.y = pack_half2(o[2], o[3]);
-        ov.z = pack_half2(o[4], o[5]);
-        ov.w = pack_half2(o[6], o[7]);
-        *reinterpret_cast<uint4*>(a.y + pix[u] * a.C + c0) = ov;
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        o[2 * j] = fmaf(f.x, A[2 * j], B[2 * j]);
+        o[2 * j + 1] = fmaf(f.y, A[2 * j + 1], B[2 * j + 1]);
       }
+      if (a.silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = silu_tanh(o[j]);
+      }
+      uint4 ov;
+      ov.x = pack_half2(o[0], o[1]);
+      ov.y = pack_half2(o[2], o[3]);
+      ov.z = pack_half2(o[4], o[5]);
+      ov.w = pack_half2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(a.y + pix * a.C + vc * 8) = ov;
+    };
+    int row = r;
+    for (; row + 3 * rpi < nrows; row += 4 * rpi) {
+      const uint4 v0 = gn_load_vec(a, pix0 + row, vc);
+      const uint4 v1 = gn_load_vec(a, pix0 + row + rpi, vc);
+      const uint4 v2 = gn_load_vec(a, pix0 + row + 2 * rpi, vc);
+      const uint4 v3 = gn_load_vec(a, pix0 + row + 3 * rpi, vc);
+      finish(v0, pix0 + row);
+      finish(v1, pix0 + row + rpi);
+      finish(v2, pix0 + row + 2 * rpi);
+      finish(v3, pix0 + row + 3 * rpi);
     }
+    for (; row < nrows; row += rpi) finish(gn_load_vec(a, pix0 + row, vc), pix0 + row);
   }
 }
-
 
 constexpr int kGn1Threads = 512;
 
@@ -367,7 +357,7 @@ inline int gn_onepass_cluster(int NB, int HW, int C) {
 }
 
 inline int gn_rows_per_cta(int C, int HW) {
-  int rows = 65536 / (C * 2);  // ~64 KB of activations per CTA
+  int rows = 49152 / (C * 2);  // ~48 KB of activations per CTA
   if (rows < 4) rows = 4;
   if (rows > HW) rows = HW;
   return rows;
@@ -618,15 +608,15 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
   a.chunks = (HW + a.rows_per_cta - 1) / a.rows_per_cta;
   const int VC = C / 8;
   const int rpi = (kGnThreads / VC) > 1 ? (kGnThreads / VC) : 1;
-  const int smem_stats = 2 * rpi * C * static_cast<int>(sizeof(float));
+  const int smem_stats = a.rows_per_cta * C * 2 + 2 * rpi * C * static_cast<int>(sizeof(float));
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kGnMaxC * 4 * 2);
+    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     attr_set = true;
   }
   dim3 grid(a.chunks, NB);
   udt_host::launch_pdl(gn_stats_kernel, dim3(grid), dim3(kGnThreads), smem_stats, st, a);
-  udt_host::launch_pdl(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 2 * C * sizeof(float), st, a);
+  udt_host::launch_pdl(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0, st, a);
   return check_launch("udt_groupnorm_nhwc");
 }
 
