@@ -47,6 +47,17 @@ def measured_peaks():
     return {"tflops": 1590.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md: 1.59 PFLOP/s, 6.65 TB/s)"}
 
 
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per udt_igemm launch (average over the launches of one UNet CFG step),
+    from the committed ncu capture of scripts/ncu_step.py (profiles/r01_step_igemm_traffic.json); None if absent"""
+    path = os.path.join(ROOT, "profiles", "r01_step_igemm_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)"""
 
@@ -217,8 +228,9 @@ def run_b200(args):
     runner = sampler.last_runner
     # kernels launched in the timed region: graph replays (captured launches per step) + eager conditioner/decoder calls
     launches = eager_calls + args.steps * DDIM_STEPS * max(runner.launches_per_step, 1)
-    # ---- per-kernel-class timing of ONE UNet CFG step, live, CUDA events on the launching stream (eager replay)
-    prof = ops.profile_step(runner, warm=2, reps=3)
+    # ---- per-kernel-class timing of ONE UNet CFG step, live: every distinct call of the step replayed back to back in
+    # a CUDA graph on the launching stream, CUDA events around the replay (ops.profile_step)
+    prof = ops.profile_step(runner, warm=2, reps=20)
     peaks = measured_peaks()
     ig = prof["by_op"].get("udt_igemm", {"ms": 0.0, "calls": 0})
     unet_step_ms = prof["step_ms_graph"]
@@ -227,8 +239,11 @@ def run_b200(args):
         flops = 2 * B * GFLOP_UNET_IGEMM * 1e9            # algorithmic FLOPs of all igemm launches of one CFG step
         ach = flops / (ig["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "udt_igemm_kernel", "achieved": ach, "peak": peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                    "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": ncu_traffic_per_launch(),
+                    "peak_source": peaks["source"] + " bf16_tflops_sustained",
                     "launches_per_unet_step": ig["calls"], "ms_per_unet_step": ig["ms"],
+                    "avg_launch_us": 1e3 * ig["ms"] / max(ig["calls"], 1),
+                    "flop_per_launch": flops / max(ig["calls"], 1),
                     "share_of_step": ig["ms"] / max(prof["step_ms_eager_sum"], 1e-9)}
 
     line = None
@@ -251,7 +266,8 @@ def run_b200(args):
                 "gpu_launches": int(launches),
                 "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "roofline": roofline,
-                "kernel_breakdown_unet_step": prof["by_op"]}
+                "kernel_breakdown_unet_step": prof["by_op"],
+                "top_calls_unet_step": prof["by_shape"][:12]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         s = cpu_reference_sample(threads)

@@ -48,36 +48,62 @@ def _invoke(name: str, *args, shape=None) -> None:
     _lib.check(rc, name)
 
 
-def profile_step(runner, warm: int = 2, reps: int = 3) -> dict:
-    """Live per-entry-point device time of ONE sampler step (udt_cfg_pack -> UNet -> udt_cfg_euler_step), measured
-    with CUDA events on the launching stream around every C-ABI call of an eager (un-graphed) replay, plus the
-    duration of the same step as a CUDA-graph replay.  The runner's state is restored afterwards."""
-    global _prof
+def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
+    """Live per-entry-point device time of ONE sampler step (udt_cfg_pack -> UNet -> udt_cfg_euler_step).
+
+    The step is executed once eagerly while every C-ABI call (function, arguments) is recorded; each distinct
+    (entry point, problem shape) is then replayed `reps` times back to back inside a CUDA graph on the launching
+    stream and timed with CUDA events around the replay (no host launch cost, no per-call event overhead, programmatic
+    dependent launch active exactly as in the product's step graph); a shape's time is multiplied by its call count.
+    Also returns the duration of the whole step as a CUDA-graph replay.  The runner's state is restored afterwards."""
+    global CALL_LOG, SHAPE_LOG
     x_saved = runner.x.clone()
     runner.row.copy_(runner.table[0:1])
     for _ in range(warm):
         runner._body()
     torch.cuda.synchronize()
+    keep = []                       # keep the logged step's temporaries alive: the recorded raw pointers stay valid
+    orig_empty = torch.empty
+
+    def empty_keep(*a, **k):
+        t = orig_empty(*a, **k)
+        keep.append(t)
+        return t
+
+    torch.empty = empty_keep
+    shape_log_prev = SHAPE_LOG
+    SHAPE_LOG, CALL_LOG = [], []
+    try:
+        runner._body()
+        torch.cuda.synchronize()
+    finally:
+        torch.empty = orig_empty
+        calls, CALL_LOG, SHAPE_LOG = CALL_LOG, None, shape_log_prev
+    groups: dict = {}
+    for name, fn, args, shape in calls:
+        groups.setdefault((name, shape), []).append((fn, args))
     acc: dict = {}
-    total = 0.0
-    for _ in range(reps):
-        _prof = []
-        try:
-            # keep the GPU busy while the host enqueues the whole step, so that the event pairs time back-to-back
-            # kernel execution instead of the host's launch cadence
-            torch.cuda._sleep(40_000_000)
-            runner._body()
-            torch.cuda.synchronize()
-            for name, e0, e1 in _prof:
-                ms = e0.elapsed_time(e1)
-                a = acc.setdefault(name, {"ms": 0.0, "calls": 0})
-                a["ms"] += ms / reps
-                a["calls"] += 1
-                total += ms / reps
-        finally:
-            _prof = None
-    for a in acc.values():
-        a["calls"] //= reps
+    shapes = []
+    for (name, shape), lst in groups.items():
+        fn, args = lst[0]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = torch.cuda.current_stream().cuda_stream
+            for _ in range(reps):
+                _lib.check(fn(*args, st), name)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        a = acc.setdefault(name, {"ms": 0.0, "calls": 0})
+        a["ms"] += ms * len(lst)
+        a["calls"] += len(lst)
+        shapes.append({"op": name, "shape": [str(v) for v in shape], "calls": len(lst), "us_per_call": 1e3 * ms})
+    total = sum(a["ms"] for a in acc.values())
     step_ms_graph = None
     if runner.graph is not None:
         for _ in range(warm):
@@ -85,13 +111,15 @@ def profile_step(runner, warm: int = 2, reps: int = 3) -> dict:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
+        for _ in range(5):
             runner.graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        step_ms_graph = e0.elapsed_time(e1) / reps
+        step_ms_graph = e0.elapsed_time(e1) / 5
     runner.x.copy_(x_saved)
-    return {"by_op": acc, "step_ms_eager_sum": total, "step_ms_graph": step_ms_graph}
+    del keep
+    shapes.sort(key=lambda r: -r["us_per_call"] * r["calls"])
+    return {"by_op": acc, "step_ms_eager_sum": total, "step_ms_graph": step_ms_graph, "by_shape": shapes}
 
 
 _SPLITK_WS = {}   # device index -> fp32 scratch for split-K partial tiles (stream ordered, shared by all calls)
