@@ -150,7 +150,7 @@ def run_reference(args):
                              "detail": timed[-1]},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    args.emit(json.dumps(line))
 
 
 # =================================================================================================== our arm
@@ -276,10 +276,24 @@ def run_b200(args):
                                           "evaluation (batch 2) + VAE decode; images/s = 1/(2 t_enc + 50 t_unet + t_dec)",
                                 "detail": s}
     if rank == 0:
-        print(json.dumps(line))
+        args.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def claim_stdout():
+    """Route everything that libraries print on fd 1 (e.g. NCCL's version banner) to stderr and return a writer for the
+    ONE JSON line the contract allows on stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+
+    def emit(line: str) -> None:
+        os.write(real, (line + "\n").encode())
+
+    return emit
 
 
 def main():
@@ -291,6 +305,10 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per request")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    relaunch = args.impl != "reference" and args.gpus != world and world == 1 and args.gpus > 1
+    if not relaunch:
+        args.emit = claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
