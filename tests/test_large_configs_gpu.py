@@ -1,0 +1,81 @@
+"""BASELINE.json configs[2] (batch 32) and configs[4] (768x768) at full network size, few sampler steps: the kernels'
+large-batch / long-sequence schedules (N = 9216 attention, 96x96 latents, batch-64 CFG tensors) against the fp32
+oracle (oracle/restated.py, pinned by oracle/make_golden.py) evaluated on the same device and seeds, plus the
+size-independent property that a request's rows do not depend on how it is sharded."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def full_engine(udt_lib):
+    from udifftext_b200 import api, synth
+    dev = torch.device("cuda", 0)
+    sd = synth.synthetic_state_dict(synth.load_manifest("full"), 1234)
+    return api.build_engine("full", dev, state_dict=sd), {k: v.to(dev) for k, v in sd.items()}
+
+
+def test_c5_768px_matches_oracle(full_engine):
+    """2 images of 768x768 (latent 96x96: self-attention over N = 9216 / 2304 / 576 / 144 keys), 3 steps, 1-12 char strings"""
+    from oracle import restated as R
+    from udifftext_b200 import api, synth
+    eng, sd_dev = full_engine
+    dev = torch.device("cuda", 0)
+    cfgs = api.runtime_config(steps=3, batch_size=2)
+    sampler = api.init_sampling(cfgs)
+    sampler.verbose = False
+    torch.manual_seed(31)
+    img, z = api.predict(cfgs, eng, sampler, synth.synthetic_batch(5, 2, 768, 768, None))
+    torch.cuda.synchronize()
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in synth.synthetic_batch(5, 2, 768, 768, None).items()}
+    torch.manual_seed(31)
+    with torch.no_grad():
+        ref_img, ref_z = R.predict(sd_dev, batch, 3, 5.0)
+    ez, ep = _rel(z, ref_z), _rel(img, ref_img)
+    print(f"C5-shape predict (768px, 3 steps): latents rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}")
+    assert tuple(img.shape) == (2, 3, 768, 768) and torch.isfinite(img).all()
+    assert ez < 1e-2 and ep < 1e-2   # fp16 storage / fp32 accumulation vs fp32
+
+
+def test_c3_batch32_rows_are_shard_independent(full_engine):
+    """batch 32 at 512x512 (CFG tensors of 64 samples), 2 steps: rows 8..12 of the request equal the same rows computed
+    as a 4-image shard of it (global RNG sliced by rank; different tile shapes / split-K choices, hence a tolerance),
+    and the first four rows match the fp32 oracle"""
+    from oracle import restated as R
+    from udifftext_b200 import api, synth
+    eng, sd_dev = full_engine
+    dev = torch.device("cuda", 0)
+    full = synth.synthetic_batch(3, 32, 512, 512, None)
+    cfg32 = api.runtime_config(steps=2, batch_size=32)
+    sampler = api.init_sampling(cfg32)
+    sampler.verbose = False
+    torch.manual_seed(41)
+    img32, z32 = api.predict(cfg32, eng, sampler, dict(full))
+    torch.cuda.synchronize()
+    assert tuple(img32.shape) == (32, 3, 512, 512) and torch.isfinite(img32).all()
+    cfg4 = api.runtime_config(steps=2, batch_size=4)
+    sub = api.shard_batch(full, 8, 12)
+    torch.manual_seed(41)
+    img4, z4 = api.predict(cfg4, eng, sampler, sub, shard=(32, 8, 12))
+    torch.cuda.synchronize()
+    e = _rel(z4, z32[8:12])
+    print(f"C3-shape predict (batch 32, 2 steps): shard rows 8..12 vs full request latents rel-L2 {e:.3e}")
+    assert e < 5e-3
+    # oracle on the first four rows: same global RNG order (posterior c, posterior uc, init noise for the WHOLE request)
+    batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
+    torch.manual_seed(41)
+    lat = (32, 4, 64, 64)
+    noise_c, noise_uc, x0 = torch.randn(lat), torch.randn(lat), torch.randn(lat)
+    first = {k: (v[:4] if isinstance(v, torch.Tensor) else (v[:4] if isinstance(v, list) else v)) for k, v in batch.items()}
+    with torch.no_grad():
+        c, uc = R.conditioner(R._sub(sd_dev, "conditioner."), first, noise_c[:4].to(dev), noise_uc[:4].to(dev), 0.18215)
+        zr = R.euler_sample(R._sub(sd_dev, "model.diffusion_model."), x0[:4].to(dev), c, uc, 2, 5.0)
+    eo = _rel(z32[:4], zr)
+    print(f"C3-shape predict: rows 0..4 vs fp32 oracle latents rel-L2 {eo:.3e}")
+    assert eo < 1e-2
