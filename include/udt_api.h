@@ -45,11 +45,11 @@ typedef struct {
   int32_t C;       /* channels consumed from this tensor (multiple of 8; each tap is zero-filled up to a multiple
                       of 64 by TMA, and the packed weight carries the same per-tap padding) */
   int32_t ld;      /* channel pitch in elements (>= C, multiple of 8) */
-  int32_t taps;    /* 1 or 9 */
+  int32_t taps;    /* 1 (point-wise), 9 (3x3 window) or 4 (2x2 window: one phase of a fused nearest-2x upsample + 3x3 conv) */
   int32_t H, W;    /* spatial size of this tensor; 0 = output size * stride */
   int32_t stride;  /* 1 or 2 (0 = 1): output pixel (y, x) reads input pixel (y*stride + ky - pad, ...) */
   int32_t pad;     /* low-side zero padding of the 3x3 window: 1 = symmetric pad 1 (openaimodel.py:132-139),
-                      0 = the VAE's pad-(0,1,0,1) downsample (model.py:77-85) */
+                      0 = the VAE's pad-(0,1,0,1) downsample (model.py:77-85); 2x2 window: 2*pad_y + pad_x (each 0 or 1) */
 } udt_gemm_src;
 
 typedef struct {
@@ -69,6 +69,9 @@ typedef struct {
   int32_t out_fp32;
   int32_t act;           /* UDT_ACT_* */
   int32_t bn_hint;       /* column tile, 0 = library picks */
+  int64_t out_stride_w, out_stride_h, out_stride_n; /* 0 = dense NHWC output; otherwise the output pixel (w, h, n)
+                            lives at out + w*stride_w + h*stride_h + n*stride_n elements (a strided view, e.g. one of the four
+                            phases of a 2x-upsampled tensor); fp16 TMA-store epilogue only, no residual */
   void* workspace;       /* optional scratch (device, 16-byte aligned) for split-K partial tiles; NULL disables split-K */
   int64_t workspace_bytes;
 } udt_igemm_desc;
@@ -80,7 +83,9 @@ typedef struct {
  * skip/nin_shortcut (openaimodel.py:240; model.py:124-126) fused as an extra K segment, nn.Linear
  * (attention.py:47,66,127-135,193-199,375,395; openaimodel.py:212-215,341-343), the `h + emb_out` add
  * (openaimodel.py:266) as `rowbias`, residual adds (openaimodel.py:268; attention.py:315-341,416) and GEGLU
- * (attention.py:49-51).  For UDT_ACT_GEGLU the logical output has N_out/2 columns (see udt_geglu_tile()). */
+ * (attention.py:49-51).  For UDT_ACT_GEGLU the logical output has N_out/2 columns (see udt_geglu_tile()).
+ * nearest-2x upsample + 3x3 conv (openaimodel.py:99-102; model.py:55-68) runs as four 2x2-window launches, one per output
+ * phase, with the 3x3 taps that fall on the same source pixel pre-summed in the weights (2.25x fewer FLOPs). */
 int udt_igemm(const udt_igemm_desc* desc, void* stream);
 /* column tile (BN) the GEGLU weight interleave must be packed for (x half then gate half per tile) */
 int udt_geglu_tile(void);

@@ -483,3 +483,20 @@ def test_fmha_rotating_buffers(udt_lib, b, n, heads):
     ref2 = F.scaled_dot_product_attention(q2, k, v).transpose(1, 2).reshape(b * n, c)
     torch.cuda.synchronize()
     assert _rel(y2.float(), ref2) < 3e-3
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout", [(2, 16, 16, 128, 128), (1, 32, 24, 64, 192), (3, 8, 8, 320, 64), (1, 64, 64, 256, 128)])
+def test_upsample_conv_as_four_phase_convs(udt_lib, nb, h, w, cin, cout):
+    """nearest-2x upsample + conv3x3 (openaimodel.py:99-102, model.py:55-68) == four 2x2-window GEMMs with pre-summed taps"""
+    from udifftext_b200 import ops, pack
+    dev = _dev()
+    g = torch.Generator().manual_seed(nb * h + cin + cout)
+    x = _randn((nb, cin, h, w), g).half()
+    wt = _randn((cout, cin, 3, 3), g, 1 / math.sqrt(9 * cin)).half()
+    b = _randn((cout,), g)
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), wt.float(), b, padding=1)
+    w4 = [t.to(dev) for t in pack.pack_conv3x3_up2(wt.float())]
+    y = ops.conv3x3_up2(x.permute(0, 2, 3, 1).contiguous().to(dev), w4, b.to(dev))
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (nb, 2 * h, 2 * w, cout)
+    assert _rel(y.permute(0, 3, 1, 2).cpu(), ref) < 2e-3

@@ -147,6 +147,16 @@ int make_tmap_nhwc_c32(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, 
   return encode(m, ptr, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+int make_tmap_nhwc_c32_strided(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t sw,
+                               uint64_t sh, uint64_t sn, uint32_t bw, uint32_t bh, uint32_t bn) {
+  if ((sw * 2) % 16 != 0 || (sh * 2) % 16 != 0 || (sn * 2) % 16 != 0)
+    return fail(UDT_ERR_ALIGN, "strided view: pixel strides must be multiples of 8 elements");
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {sw * 2, sh * 2, sn * 2};
+  cuuint32_t box[4] = {32, bw, bh, bn};
+  return encode(m, ptr, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 }  // namespace udt_host
 
 extern "C" {

@@ -49,4 +49,8 @@ int make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint
 int make_tmap_nhwc_c32(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld,
                        uint32_t bw, uint32_t bh, uint32_t bn);
 
+// same boxes over a strided pixel view: pixel (w, h, n) at element offset w*sw + h*sh + n*sn (all multiples of 8)
+int make_tmap_nhwc_c32_strided(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t sw,
+                               uint64_t sh, uint64_t sn, uint32_t bw, uint32_t bh, uint32_t bn);
+
 }  // namespace udt_host

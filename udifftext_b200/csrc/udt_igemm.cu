@@ -319,8 +319,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           const int kc = p.seg_kc[s];
           const int sw0 = tc.w0 * p.seg_stride[s], sh0 = tc.h0 * p.seg_stride[s];
           for (int t = 0; t < taps; ++t) {
-            const int dy = (taps == 9) ? (t / 3 - p.seg_pad[s]) : 0;
-            const int dx = (taps == 9) ? (t % 3 - p.seg_pad[s]) : 0;
+            // 3x3 window: (ky, kx) - pad;  2x2 window (one phase of a fused nearest-2x upsample conv): pad = 2*pad_y + pad_x
+            const int dy = (taps == 9) ? (t / 3 - p.seg_pad[s]) : (taps == 4 ? ((t >> 1) - (p.seg_pad[s] >> 1)) : 0);
+            const int dx = (taps == 9) ? (t % 3 - p.seg_pad[s]) : (taps == 4 ? ((t & 1) - (p.seg_pad[s] & 1)) : 0);
             for (int c = 0; c < kc; ++c, ++kstep) {
               if (kstep < wi.k0 || kstep >= wi.k1) continue;   // another split's K range
               mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -977,6 +978,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   int ksplit = 1, kper = ksteps_est;
   static const int split_env = env_int("UDT_IGEMM_SPLITK", 1);
   if (split_env != 0 && d->bn_hint == 0 && act == UDT_ACT_NONE && !d->out_fp32 && d->workspace != nullptr && N_out % 8 == 0 &&
+      d->out_stride_w == 0 &&
       N_out >= 64 && d->ldo % 8 == 0 && (d->residual == nullptr || d->ldr % 8 == 0) &&
       ((reinterpret_cast<uintptr_t>(d->out) | reinterpret_cast<uintptr_t>(d->residual)) & 15) == 0) {
     const int units = pair ? sms / 2 : sms;
@@ -1024,7 +1026,8 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
     const int st = a.stride > 0 ? a.stride : 1;
     const int Hs = a.H > 0 ? a.H : H * st, Ws = a.W > 0 ? a.W : W * st;
     if (a.C < 8 || a.C % 8 != 0) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d has C=%d (multiple of 8 required)", s, a.C);
-    if (a.taps != 1 && a.taps != 9) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d taps=%d (1 or 9)", s, a.taps);
+    if (a.taps != 1 && a.taps != 9 && a.taps != 4) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d taps=%d (1, 4 or 9)", s, a.taps);
+    if (a.taps == 4 && (a.pad < 0 || a.pad > 3 || st != 1)) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d: 2x2 window needs pad in 0..3 (2*pad_y + pad_x), stride 1", s);
     if (a.ld < a.C) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d ld=%d < C=%d", s, a.ld, a.C);
     if (a.taps == 9 && a.pad != 0 && a.pad != 1) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d pad=%d (0 or 1)", s, a.pad);
     if (a.taps == 1 && st != 1) return fail(UDT_ERR_SHAPE, "udt_igemm: segment %d: point-wise segments must have stride 1", s);
@@ -1050,13 +1053,19 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
                          (d->residual == nullptr || (((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && d->ldr % 8 == 0));
   const int n_logical = act == UDT_ACT_GEGLU ? N_out / 2 : N_out;
   p.staged = (ksplit == 1 && !d->out_fp32 && BN >= 32 && aligned16 && n_logical >= 8) ? 1 : 0;
+  if (d->out_stride_w > 0 && (!p.staged || d->residual != nullptr || d->out_stride_w % 8 || d->out_stride_h % 8 || d->out_stride_n % 8))
+    return fail(UDT_ERR_SHAPE, "udt_igemm: a strided output view needs the TMA-store epilogue (fp16, >= 8 columns), no residual, strides %% 8 == 0");
   int epi_bytes = 0;
   if (p.staged) {
     // every epilogue warp stores its own 32-row slab of the tile: a {sbw, sbh, sbn} pixel box
     const int sbw = p.bw < 32 ? p.bw : 32;
     const int sbh = p.bh < 32 / sbw ? p.bh : 32 / sbw;
     const int sbn = 32 / (sbw * sbh);
-    rc = make_tmap_nhwc_c32(&p.mapOut, d->out, static_cast<uint64_t>(n_logical), W, H, NB, d->ldo, sbw, sbh, sbn);
+    if (d->out_stride_w > 0)   // strided output view (one phase of the 2x-upsampled output)
+      rc = make_tmap_nhwc_c32_strided(&p.mapOut, d->out, static_cast<uint64_t>(n_logical), W, H, NB, d->out_stride_w,
+                                      d->out_stride_h, d->out_stride_n, sbw, sbh, sbn);
+    else
+      rc = make_tmap_nhwc_c32(&p.mapOut, d->out, static_cast<uint64_t>(n_logical), W, H, NB, d->ldo, sbw, sbh, sbn);
     if (rc != UDT_OK) return rc;
     // short-K GEMMs are epilogue-bound: two epilogue warpgroups and deeper chunk buffering; long-K tiles hide a
     // single group's epilogue behind the mainloop and keep the shared memory for operand stages instead

@@ -32,7 +32,8 @@ class IGemmDesc(Structure):
     _fields_ = [("src", GemmSrc * 3), ("nsrc", c_int32), ("NB", c_int32), ("H", c_int32), ("W", c_int32),
                 ("weight", c_void_p), ("ldw", c_int32), ("N_out", c_int32), ("bias", c_void_p), ("rowbias", c_void_p),
                 ("ld_rowbias", c_int32), ("residual", c_void_p), ("ldr", c_int32), ("out", c_void_p), ("ldo", c_int32),
-                ("out_fp32", c_int32), ("act", c_int32), ("bn_hint", c_int32), ("workspace", c_void_p),
+                ("out_fp32", c_int32), ("act", c_int32), ("bn_hint", c_int32), ("out_stride_w", c_int64), ("out_stride_h", c_int64),
+                ("out_stride_n", c_int64), ("workspace", c_void_p),
                 ("workspace_bytes", c_int64)]
 
 

@@ -47,6 +47,31 @@ def pack_conv3x3_padded(w_oihw: torch.Tensor, kpad: int) -> torch.Tensor:
     return out
 
 
+def pack_conv3x3_up2(w_oihw: torch.Tensor) -> list:
+    """nearest-2x upsample followed by a 3x3 conv (pad 1) == four 2x2 convs on the LOW-resolution input, one per output
+    phase (py, px): output pixel (2h+py, 2w+px) reads source rows {h-1, h} (py = 0) or {h, h+1} (py = 1), and the 3x3 taps
+    that land on the same source pixel are summed (in fp32, then rounded to fp16).  Returns the 4 packed weights
+    [O, 4*I64] in phase order (0,0), (0,1), (1,0), (1,1), K ordered (tap = ty*2 + tx, channel padded to 64)."""
+    o, i, kh, kw = w_oihw.shape
+    assert (kh, kw) == (3, 3)
+    w = w_oihw.float()
+    i64 = _pad64(i)
+    taps = {0: ([0], [1, 2]), 1: ([0, 1], [2])}     # phase -> (3x3 indices feeding window slot 0, slot 1)
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            wp = w.new_zeros((o, 2, 2, i64))
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = 0
+                    for ky in taps[py][ty]:
+                        for kx in taps[px][tx]:
+                            acc = acc + w[:, :, ky, kx]
+                    wp[:, ty, tx, :i] = acc
+            out.append(wp.reshape(o, 4 * i64).to(torch.float16).contiguous())
+    return out
+
+
 def pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[out, in] (or 1x1 conv [O, I, 1, 1]) -> fp16 [out, round_up(in, 64)]"""
     return _pad_k(w.reshape(w.shape[0], -1)).to(torch.float16).contiguous()

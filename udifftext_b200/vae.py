@@ -126,7 +126,8 @@ class VAEB200:
             item = {"blocks": blocks, "up": None}
             k = f"decoder.up.{lvl}.upsample.conv."
             if k + "weight" in sd:
-                item["up"] = (pack.pack_conv3x3(sd[k + "weight"]).to(dev), pack.f32(sd[k + "bias"]).to(dev))
+                item["up"] = ([t.to(dev) for t in pack.pack_conv3x3_up2(sd[k + "weight"])], pack.f32(sd[k + "bias"]).to(dev),
+                              pack.pack_conv3x3(sd[k + "weight"]).to(dev))
             self.d_up.append(item)
         self.d_g, self.d_b = pack.f32(sd["decoder.norm_out.weight"]).to(dev), pack.f32(sd["decoder.norm_out.bias"]).to(dev)
         self.d_w_out = pack.pack_conv3x3(sd["decoder.conv_out.weight"]).to(dev)
@@ -205,8 +206,8 @@ class VAEB200:
             for r in item["blocks"]:
                 h = self._res(r, h)
             if item["up"] is not None:                             # nearest x2 + conv3x3 (model.py:55-68)
-                w, b = item["up"]
-                h = ops.conv3x3(ops.upsample2x(h), w, b)
+                w4, b, wf = item["up"]
+                h = ops.conv3x3_up2(h, w4, b, w_full=wf)                      # four 2x2 phase convs on the low-res tensor
         a = self._gn(h, self.d_g, self.d_b, True)
         nb, oh, ow, _ = a.shape
         out = torch.empty((nb, oh, ow, 4), device=self.device, dtype=torch.float32)
