@@ -72,6 +72,8 @@ typedef struct {
   int64_t out_stride_w, out_stride_h, out_stride_n; /* 0 = dense NHWC output; otherwise the output pixel (w, h, n)
                             lives at out + w*stride_w + h*stride_h + n*stride_n elements (a strided view, e.g. one of the four
                             phases of a 2x-upsampled tensor); fp16 TMA-store epilogue only, no residual */
+  int32_t weight_img_rows; /* 0 = one weight [N_out, ldw] for all images; > 0 = per-image weights: image i uses rows
+                            [i * weight_img_rows, i * weight_img_rows + N_out) of `weight` (>= 128 pixels per image) */
   void* workspace;       /* optional scratch (device, 16-byte aligned) for split-K partial tiles; NULL disables split-K */
   int64_t workspace_bytes;
 } udt_igemm_desc;
@@ -130,6 +132,20 @@ int udt_label_embed(const int32_t* idx, const float* emb, const float* pe, void*
                     int32_t D, void* stream);
 int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int32_t heads, int32_t dh, int32_t ld, int32_t ldo,
                   float scale, void* stream);
+
+/* Folded textual cross-attention (attention.py:140-174 with the step-invariant K / V of the 12 context tokens folded into
+ * the projections; exact in real arithmetic):
+ *   scores[m, h*L + l] = LN(t)[m, :] . W1[s(m)][h*L + l, :],   W1[s][h*L + l, c] = scale * sum_d K[s, l, h*64 + d] * Wq[h*64 + d, c]
+ *   out[m, :]          = P[m, :] . W2[s(m)]^T + bias,           W2[s][c, h*L + l]  = sum_d Wo[c, h*64 + d] * V[s, l, h*64 + d]
+ * udt_xattn_fold builds W1 [B, Npad, C] and W2 [B, C, Npad] (fp16, Npad = heads*L rounded up to 64, pad rows / columns 0)
+ * from kc / vc fp16 [B, L, ldkv] (head h at columns [h*64, h*64+64)), wq / wo fp16 [C, ldwq] / [C, ldwo] (C = heads*64);
+ * the two GEMMs run through udt_igemm with per-image weights; udt_softmax_groups turns the scores into probabilities:
+ * in / out fp16 [rows, ld] (may alias), `groups` groups of L consecutive columns per row, columns >= groups*L of `out` are
+ * zeroed up to `cols`; optional fp32 export probs[(img*groups + g), n, l] with rows = imgs * N (the reference's attn_map). */
+int udt_xattn_fold(const void* kc, const void* vc, int32_t ldkv, const void* wq, int32_t ldwq, const void* wo, int32_t ldwo,
+                   void* w1, void* w2, int32_t B, int32_t L, int32_t heads, int32_t Npad, float scale, void* stream);
+int udt_softmax_groups(const void* in, void* out, int32_t rows, int32_t cols, int32_t ld, int32_t groups, int32_t L,
+                       float* probs, int32_t N, void* stream);
 
 /* row-wise softmax over fp16 [rows, cols] in place with a pre-scale (VAE single-head attention,
  * model.py:246-248, executed as GEMM -> softmax -> GEMM). */

@@ -500,3 +500,37 @@ def test_upsample_conv_as_four_phase_convs(udt_lib, nb, h, w, cin, cout):
     torch.cuda.synchronize()
     assert tuple(y.shape) == (nb, 2 * h, 2 * w, cout)
     assert _rel(y.permute(0, 3, 1, 2).cpu(), ref) < 2e-3
+
+
+@pytest.mark.parametrize("b,n,heads,l", [(2, 256, 5, 12), (1, 1024, 10, 12), (3, 256, 20, 7)])
+def test_folded_cross_attention_matches_direct(udt_lib, b, n, heads, l):
+    """t_attn with the context folded into to_q / to_out (udt_xattn_fold + per-sample-weight GEMMs + grouped softmax)
+    against the direct formulation in fp32 torch (attention.py:140-174)"""
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(b * n + heads)
+    c = heads * 64
+    x = _randn((b * n, c), g).half()                       # LN(t)
+    wq = _randn((c, c), g, 1 / math.sqrt(c)).half()
+    wo = _randn((c, c), g, 1 / math.sqrt(c)).half()
+    bo = _randn((c,), g)
+    k = _randn((b * l, c), g).half()
+    v = _randn((b * l, c), g).half()
+    res = _randn((b * n, c), g).half()
+    q = (x.float() @ wq.float().t()).view(b, n, heads, 64).transpose(1, 2)
+    kk = k.float().view(b, l, heads, 64).transpose(1, 2)
+    vv = v.float().view(b, l, heads, 64).transpose(1, 2)
+    pr = torch.softmax(q @ kk.transpose(-1, -2) * 0.125, dim=-1)
+    ref = (pr @ vv).transpose(1, 2).reshape(b * n, c) @ wo.float().t() + bo + res.float()
+    npad = (heads * l + 63) // 64 * 64
+    w1 = torch.empty((b, npad, c), device=dev, dtype=torch.float16)
+    w2 = torch.empty((b, c, npad), device=dev, dtype=torch.float16)
+    ops.xattn_fold(k.to(dev), v.to(dev), wq.to(dev), wo.to(dev), b, l, heads, 0.125, w1, w2)
+    sc = ops.linear(x.to(dev), w1.view(b * npad, c), groups=b, weight_img_rows=npad)
+    probs = torch.empty((b * heads, n, l), device=dev, dtype=torch.float32)
+    ops.softmax_groups(sc, heads, l, probs=probs, n=n)
+    t = res.to(dev).clone()
+    ops.linear(sc, w2.view(b * c, npad), bo.to(dev), residual=t, out=t, groups=b, weight_img_rows=c)
+    torch.cuda.synchronize()
+    assert _rel(t.cpu(), ref) < 3e-3
+    assert (probs.cpu() - pr.reshape(b * heads, n, l)).abs().max().item() < 5e-3

@@ -102,6 +102,96 @@ __global__ void __launch_bounds__(kXaThreads) xattn_small_l_kernel(const __half*
   }
 }
 
+// ---------------------------------------------------------------------------------------------- folded cross-attention
+// W1[s][h*L + l][c] = scale * sum_d K[s,l,h*64+d] * Wq[h*64+d][c];  W2[s][c][h*L + l] = sum_d Wo[c][h*64+d] * V[s,l,h*64+d]
+// (once per request: the context is step-invariant).  One thread per output element, 64-term dot products.
+__global__ void __launch_bounds__(256) xattn_fold_kernel(const __half* __restrict__ kc, const __half* __restrict__ vc, int ldkv,
+                                                         const __half* __restrict__ wq, int ldwq,
+                                                         const __half* __restrict__ wo, int ldwo, __half* __restrict__ w1,
+                                                         __half* __restrict__ w2, int B, int L, int heads, int Npad,
+                                                         float scale) {
+  griddep_launch();
+  griddep_wait();
+  const int C = heads * 64;
+  const long long per = static_cast<long long>(Npad) * C;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= 2 * per * B) return;
+  const bool second = idx >= per * B;
+  const long long i = second ? idx - per * B : idx;
+  const int s = static_cast<int>(i / per);
+  const int r = static_cast<int>(i - s * per);
+  if (!second) {                       // W1[s][row = h*L + l][c]
+    const int row = r / C, c = r - row * C;
+    float acc = 0.0f;
+    if (row < heads * L) {
+      const int h = row / L, l = row - h * L;
+      const __half* kp = kc + (static_cast<size_t>(s) * L + l) * ldkv + h * 64;
+      for (int d = 0; d < 64; ++d) acc = fmaf(__half2float(kp[d]), __half2float(wq[static_cast<size_t>(h * 64 + d) * ldwq + c]), acc);
+      acc *= scale;
+    }
+    w1[i] = __float2half_rn(acc);
+  } else {                             // W2[s][c][col = h*L + l]
+    const int c = r / Npad, col = r - c * Npad;
+    float acc = 0.0f;
+    if (col < heads * L) {
+      const int h = col / L, l = col - h * L;
+      const __half* vp = vc + (static_cast<size_t>(s) * L + l) * ldkv + h * 64;
+      const __half* wp = wo + static_cast<size_t>(c) * ldwo + h * 64;
+      for (int d = 0; d < 64; ++d) acc = fmaf(__half2float(wp[d]), __half2float(vp[d]), acc);
+    }
+    w2[i] = __float2half_rn(acc);
+  }
+}
+
+// softmax over `groups` groups of L <= 16 consecutive columns of every row; one thread per (row, group)
+__global__ void __launch_bounds__(256) softmax_groups_kernel(const __half* __restrict__ in, __half* __restrict__ out, int rows,
+                                                             int cols, int ld, int groups, int L, float* __restrict__ probs,
+                                                             int N) {
+  griddep_launch();
+  griddep_wait();
+  const int gpr = groups + 1;          // the extra "group" of a row zeroes the pad columns
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * gpr) return;
+  const int row = static_cast<int>(idx / gpr);
+  const int g = static_cast<int>(idx - static_cast<long long>(row) * gpr);
+  if (g == groups) {
+    for (int c = groups * L; c < cols; ++c) out[static_cast<size_t>(row) * ld + c] = __float2half_rn(0.0f);
+    return;
+  }
+  const __half* x = in + static_cast<size_t>(row) * ld + g * L;
+  float v[16];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    v[l] = (l < L) ? __half2float(x[l]) : -INFINITY;
+    mx = fmaxf(mx, v[l]);
+  }
+  float sum = 0.0f;
+  if (L > 1) {
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      v[l] = (l < L) ? __expf(v[l] - mx) : 0.0f;
+      sum += v[l];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) v[l] *= inv;
+  } else {
+    v[0] = 1.0f / (1.0f + __expf(-v[0]));   // sigmoid on a single token (attention.py:159-162)
+  }
+  __half* y = out + static_cast<size_t>(row) * ld + g * L;
+#pragma unroll
+  for (int l = 0; l < 16; ++l)
+    if (l < L) y[l] = __float2half_rn(v[l]);
+  if (probs != nullptr) {
+    const int img = row / N, n = row - img * N;
+    float* pr = probs + ((static_cast<size_t>(img) * groups + g) * N + n) * L;
+#pragma unroll
+    for (int l = 0; l < 16; ++l)
+      if (l < L) pr[l] = v[l];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- LabelEncoder pieces
 // Character embedding + sinusoid positional encoding (encoders/modules.py:1160-1166, 1083-1085):
 // out fp16 [B*L, D] = emb[idx[b,l], :] + pe[l, :]
@@ -492,6 +582,34 @@ extern "C" int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld,
   udt_host::launch_pdl(softmax_rows_kernel, dim3(rows), dim3(kSmThreads), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__half*>(x), cols,
                                                                                        ld, scale);
   return check_launch("udt_softmax_rows");
+}
+
+extern "C" int udt_xattn_fold(const void* kc, const void* vc, int32_t ldkv, const void* wq, int32_t ldwq, const void* wo,
+                              int32_t ldwo, void* w1, void* w2, int32_t B, int32_t L, int32_t heads, int32_t Npad, float scale,
+                              void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (B < 1 || L < 1 || L > 16 || heads < 1 || Npad < heads * L || Npad % 8) return fail(UDT_ERR_SHAPE, "udt_xattn_fold: bad shape");
+  const long long total = 2LL * B * Npad * heads * 64;
+  udt_host::launch_pdl(xattn_fold_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                       reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __half*>(kc),
+                       reinterpret_cast<const __half*>(vc), ldkv, reinterpret_cast<const __half*>(wq), ldwq,
+                       reinterpret_cast<const __half*>(wo), ldwo, reinterpret_cast<__half*>(w1), reinterpret_cast<__half*>(w2), B, L,
+                       heads, Npad, scale);
+  return check_launch("udt_xattn_fold");
+}
+
+extern "C" int udt_softmax_groups(const void* in, void* out, int32_t rows, int32_t cols, int32_t ld, int32_t groups, int32_t L,
+                                  float* probs, int32_t N, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (rows < 1 || groups < 1 || L < 1 || L > 16 || groups * L > cols || cols > ld || (probs != nullptr && (N < 1 || rows % N)))
+    return fail(UDT_ERR_SHAPE, "udt_softmax_groups: bad shape");
+  const long long total = static_cast<long long>(rows) * (groups + 1);
+  udt_host::launch_pdl(softmax_groups_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                       reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out),
+                       rows, cols, ld, groups, L, probs, N);
+  return check_launch("udt_softmax_groups");
 }
 
 extern "C" int udt_cfg_pack(const float* x, const float* concat_uc, const float* concat_c, void* unet_in, int32_t B,

@@ -69,6 +69,7 @@ struct IGemmParams {
   int32_t ksplit, kper;
   uint32_t mg_s;
   long long split_stride;
+  int32_t b_img_rows;     // per-image weights: image i reads weight rows [i * b_img_rows, ...) (0 = one shared weight)
   int32_t N_out, BN, stages;
   const float* bias;
   const float* rowbias;
@@ -356,7 +357,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       const uint32_t full0 = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
       for (int wk = tile0; wk < p.num_tiles; wk += tile_step) {
         const WorkItem wi = decode_work(p, wk);
-        const int n_row = (wi.tile - fast_div(wi.tile, p.mg_n, p.tiles_n) * p.tiles_n) * p.BN + rank * b_rows;
+        int n_row = (wi.tile - fast_div(wi.tile, p.mg_n, p.tiles_n) * p.tiles_n) * p.BN + rank * b_rows;
+        if (p.b_img_rows > 0) n_row += decode_tile<kPair>(p, wi.tile, rank).n0 * p.b_img_rows;   // this tile's image
         for (int k = wi.k0; k < wi.k1; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (issuer) {
@@ -978,7 +980,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   int ksplit = 1, kper = ksteps_est;
   static const int split_env = env_int("UDT_IGEMM_SPLITK", 1);
   if (split_env != 0 && d->bn_hint == 0 && act == UDT_ACT_NONE && !d->out_fp32 && d->workspace != nullptr && N_out % 8 == 0 &&
-      d->out_stride_w == 0 &&
+      d->out_stride_w == 0 && d->weight_img_rows == 0 &&
       N_out >= 64 && d->ldo % 8 == 0 && (d->residual == nullptr || d->ldr % 8 == 0) &&
       ((reinterpret_cast<uintptr_t>(d->out) | reinterpret_cast<uintptr_t>(d->residual)) & 15) == 0) {
     const int units = pair ? sms / 2 : sms;
@@ -1044,7 +1046,16 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   const int kdim_b = (nsrc == 1 && d->src[0].taps == 1) ? d->src[0].C : ktotal;
   const int ldw = d->ldw > 0 ? d->ldw : kdim_b;
   if (ldw < kdim_b) return fail(UDT_ERR_SHAPE, "udt_igemm: ldw=%d < K=%d (conv weights must be packed per 64-channel block)", ldw, kdim_b);
-  rc = make_tmap_2d(&p.mapB, d->weight, static_cast<uint64_t>(kdim_b), static_cast<uint64_t>(N_out),
+  p.b_img_rows = 0;
+  uint64_t w_rows = static_cast<uint64_t>(N_out);
+  if (d->weight_img_rows > 0) {
+    // per-image weights (folded cross-attention): a tile must lie inside one image, and so must a CTA pair
+    if (p.bn != 1 || d->weight_img_rows < N_out || (pair && ((p.tiles_w * p.tiles_h) & 1)))
+      return fail(UDT_ERR_SHAPE, "udt_igemm: per-image weights need >= 128 (pairs: a multiple of 256) pixels per image");
+    p.b_img_rows = d->weight_img_rows;
+    w_rows = static_cast<uint64_t>(d->weight_img_rows) * NB;
+  }
+  rc = make_tmap_2d(&p.mapB, d->weight, static_cast<uint64_t>(kdim_b), w_rows,
                     static_cast<uint64_t>(ldw), 64, static_cast<uint32_t>(b_rows));
   if (rc != UDT_OK) return rc;
 

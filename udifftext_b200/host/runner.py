@@ -41,6 +41,7 @@ class StepRunner:
         self.table: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
+        self.fold: Optional[Dict[int, tuple]] = None   # folded t_attn weights of the conditional half (UNetB200.fold_context)
         self.skip_uc = False       # this request's unconditional context is all zeros (UNetB200.skip_uc_xattn)
 
     # ------------------------------------------------------------------------------------------ per request
@@ -58,6 +59,8 @@ class StepRunner:
         if skip != self.skip_uc:
             self.skip_uc = skip
             self.graph = None          # the captured step depends on the flag
+        if skip:                       # conditional half: context folded into the t_attn projections (static buffers)
+            self.fold = u.fold_context(self.kv, self.ctx_len, self.B, self.B, self.fold)
         k = step_constants(denoiser, sigmas, s_churn, s_tmin, s_tmax)
         if float(k["gamma"].abs().max()) != 0.0:
             raise NotImplementedError("s_churn > 0 (stochastic sampling) is not used by UDiffText (util.py:39)")
@@ -77,6 +80,7 @@ class StepRunner:
         prev = u.export_attn_maps
         u.export_attn_maps = export
         u.skip_uc_xattn = self.skip_uc
+        u.xattn_fold = self.fold if self.skip_uc else None
         try:
             u.forward_nhwc(self.unet_in, self.row[:, :ew].expand(2 * self.B, ew), self.kv, self.ctx_len, out=self.eps)
         finally:

@@ -33,7 +33,7 @@ class IGemmDesc(Structure):
                 ("weight", c_void_p), ("ldw", c_int32), ("N_out", c_int32), ("bias", c_void_p), ("rowbias", c_void_p),
                 ("ld_rowbias", c_int32), ("residual", c_void_p), ("ldr", c_int32), ("out", c_void_p), ("ldo", c_int32),
                 ("out_fp32", c_int32), ("act", c_int32), ("bn_hint", c_int32), ("out_stride_w", c_int64), ("out_stride_h", c_int64),
-                ("out_stride_n", c_int64), ("workspace", c_void_p),
+                ("out_stride_n", c_int64), ("weight_img_rows", c_int32), ("workspace", c_void_p),
                 ("workspace_bytes", c_int64)]
 
 
@@ -58,6 +58,9 @@ _PROTOTYPES = {
     "udt_label_embed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "udt_mha_small": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "udt_softmax_rows": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "udt_xattn_fold": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32,
+                                 c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "udt_softmax_groups": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "udt_cfg_pack": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "udt_cfg_euler_step": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p]),
     "udt_vae_sample_pack": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,

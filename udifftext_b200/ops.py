@@ -163,6 +163,7 @@ def igemm(
     bn_hint: int = 0,
     out_ptr: Optional[int] = None,
     out_strides: Optional[Tuple[int, int, int]] = None,
+    weight_img_rows: int = 0,
 ) -> torch.Tensor:
     """Segmented implicit GEMM (udt_igemm).  `srcs` = [(tensor, C, ld, taps[, stride, pad, H_in, W_in]), ...];
     (nb, h, w) are the OUTPUT pixel dims; 3x3 segments default to stride 1 / pad 1."""
@@ -181,6 +182,7 @@ def igemm(
     d.ld_rowbias = 0 if rowbias is None else (n_out if ld_rowbias is None else ld_rowbias)
     d.residual, d.ldr = _ptr(residual), ldr
     d.out, d.ldo, d.out_fp32, d.act, d.bn_hint = out.data_ptr(), ldo, int(out_fp32), act, bn_hint
+    d.weight_img_rows = weight_img_rows
     if out_strides is not None:       # strided output view (element strides of w, h, n), base pointer `out_ptr`
         d.out = out_ptr
         d.out_stride_w, d.out_stride_h, d.out_stride_n = out_strides
@@ -197,23 +199,25 @@ def igemm(
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, act: int = UDT_ACT_NONE,
-           out_fp32: bool = False, bn_hint: int = 0, rowbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+           out_fp32: bool = False, bn_hint: int = 0, rowbias: Optional[torch.Tensor] = None, groups: int = 1,
+           weight_img_rows: int = 0) -> torch.Tensor:
     """y[M, N] = act(x[M, K] @ weight[N, K]^T + bias) (+ residual); fp16 in, fp16 (or fp32) out.  `x` and `weight`
     may be row-strided 2-D views (unit column stride).  `rowbias` fp32 [G, N] adds row g to the g-th block of M / G
-    consecutive rows (a per-sample bias)."""
+    consecutive rows (a per-sample bias).  `weight_img_rows` > 0: the g-th of `groups` row blocks multiplies with weight rows
+    [g * weight_img_rows, g * weight_img_rows + N) (per-sample weights, N = weight_img_rows)."""
     m, k = x.shape
-    n = weight.shape[0]
+    n = weight_img_rows if weight_img_rows > 0 else weight.shape[0]
     n_log = n // 2 if act == UDT_ACT_GEGLU else n
     if act == UDT_ACT_GEGLU and bn_hint == 0:
         from .pack import GEGLU_TILE
         bn_hint = GEGLU_TILE          # the column interleave the weight was packed with
     if out is None:
         out = torch.empty((m, n_log), device=x.device, dtype=torch.float32 if out_fp32 else torch.float16)
-    g = 1 if rowbias is None else rowbias.shape[0]
+    g = groups if rowbias is None else rowbias.shape[0]
     assert m % g == 0
     return igemm([(x, k, x.stride(0), 1)], g, 1, m // g, weight, n, out, out.stride(0), bias=bias, residual=residual,
                  ldr=0 if residual is None else residual.stride(0), out_fp32=out_fp32, act=act, bn_hint=bn_hint,
-                 rowbias=rowbias, ld_rowbias=None if rowbias is None else rowbias.stride(0))
+                 rowbias=rowbias, ld_rowbias=None if rowbias is None else rowbias.stride(0), weight_img_rows=weight_img_rows)
 
 
 def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -304,6 +308,25 @@ def xattn_small_l(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, b: int, n
         out = torch.empty((b * n, heads * 64), device=q.device, dtype=torch.float16)
     _invoke("udt_xattn_small_l", q.data_ptr(), kc.data_ptr(), vc.data_ptr(), out.data_ptr(), _ptr(probs), b, n, l, heads,
                              q.stride(0), kc.stride(0), out.stride(0), float(scale))
+    return out
+
+
+def xattn_fold(kc: torch.Tensor, vc: torch.Tensor, wq: torch.Tensor, wo: torch.Tensor, b: int, l: int, heads: int,
+               scale: float, w1: torch.Tensor, w2: torch.Tensor) -> None:
+    """fold the step-invariant context K / V (fp16 views [b*l, heads*64]) into the t_attn projections:
+    w1 fp16 [b, npad, C] (scores = LN(t) @ w1^T), w2 fp16 [b, C, npad] (out = P @ w2^T); see include/udt_api.h"""
+    npad = w1.shape[1]
+    _invoke("udt_xattn_fold", kc.data_ptr(), vc.data_ptr(), kc.stride(0), wq.data_ptr(), wq.stride(0), wo.data_ptr(),
+            wo.stride(0), w1.data_ptr(), w2.data_ptr(), b, l, heads, npad, float(scale))
+
+
+def softmax_groups(x: torch.Tensor, groups: int, l: int, out: Optional[torch.Tensor] = None,
+                   probs: Optional[torch.Tensor] = None, n: int = 0) -> torch.Tensor:
+    """x fp16 [rows, cols]: softmax over `groups` groups of `l` consecutive columns, pad columns zeroed (in place by default)"""
+    rows, cols = x.shape
+    if out is None:
+        out = x
+    _invoke("udt_softmax_groups", x.data_ptr(), out.data_ptr(), rows, cols, x.stride(0), groups, l, _ptr(probs), n)
     return out
 
 

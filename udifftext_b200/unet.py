@@ -185,6 +185,9 @@ class UNetB200:
         # (iii)).  The runner sets this flag per request after checking the context; the uc half then skips
         # t_norm / to_q / attention / to_out and receives the bias through the previous GEMM's per-sample bias.
         self.skip_uc_xattn = False
+        # per-request folded t_attn weights {layer index: (W1 [B, npad, C], W2 [B, C, npad])} of the conditional half
+        # (fold_context), or None: the runner owns the buffers and sets this before every forward
+        self.xattn_fold: Optional[Dict[int, tuple]] = None
 
     # ------------------------------------------------------------------------------------------ pieces
     def _ws(self, nb: int) -> torch.Tensor:
@@ -211,6 +214,23 @@ class UNetB200:
         ctx = t_context.to(self.device).reshape(nb * l, d).half().contiguous()
         return ops.linear(ctx, self.w_kv, out=out)
 
+    def fold_context(self, kv: torch.Tensor, ctx_len: int, first: int, count: int,
+                     bufs: Optional[Dict[int, tuple]] = None) -> Dict[int, tuple]:
+        """fold the context K / V of samples [first, first + count) (rows of `kv` from context_kv) into every t_attn layer's
+        to_q / to_out (udt_xattn_fold; once per request — the context does not change from step to step)"""
+        out: Dict[int, tuple] = {} if bufs is None else bufs
+        for li, s in enumerate(self.st_layers):
+            c = s.c
+            npad = _round_up(s.heads * ctx_len, 64)
+            if li not in out:
+                out[li] = (torch.empty((count, npad, c), device=self.device, dtype=torch.float16),
+                           torch.empty((count, c, npad), device=self.device, dtype=torch.float16))
+            w1, w2 = out[li]
+            kc = kv[first * ctx_len:, s.kv_off: s.kv_off + c]
+            vc = kv[first * ctx_len:, s.kv_off + c: s.kv_off + 2 * c]
+            ops.xattn_fold(kc, vc, s.w_tq, s.w_to, count, ctx_len, s.heads, 0.125, w1, w2)
+        return out
+
     def _res(self, r: _Res, x0: torch.Tensor, x1: Optional[torch.Tensor], rowbias: torch.Tensor) -> torch.Tensor:
         nb = x0.shape[0]
         a = ops.groupnorm(x0, r.g1, r.b1, 1e-5, True, x1=x1, ws=self._ws(nb))
@@ -234,11 +254,21 @@ class UNetB200:
             t = ops.linear(a, s.w_o1, s.b_o1, residual=t, rowbias=s.uc_rowbias(nb))   # uc half: + t_attn.to_out.bias
             hb = nb // 2
             tc = t[hb * n:]                                                            # conditional half, in place
-            q = ops.linear(ops.layernorm(tc, s.lnt_g, s.lnt_b), s.w_tq)
-            kc = kv[hb * ctx_len:, s.kv_off: s.kv_off + c]
-            vc = kv[hb * ctx_len:, s.kv_off + c: s.kv_off + 2 * c]
-            a = ops.xattn_small_l(q, kc, vc, hb, n, ctx_len, s.heads, 0.125)
-            ops.linear(a, s.w_to, s.b_to, residual=tc, out=tc)
+            fold = self.xattn_fold.get(li) if self.xattn_fold is not None else None
+            if fold is not None and n % 256 == 0:
+                # folded form: scores = LN(t) W1[s]^T, P = softmax over the 12 tokens of every head, out = P W2[s]^T
+                # (W1 / W2 = the step-invariant context K / V folded into to_q / to_out once per request)
+                w1, w2 = fold
+                npad = w1.shape[1]
+                sc = ops.linear(ops.layernorm(tc, s.lnt_g, s.lnt_b), w1.view(hb * npad, c), groups=hb, weight_img_rows=npad)
+                ops.softmax_groups(sc, s.heads, ctx_len)
+                ops.linear(sc, w2.view(hb * c, npad), s.b_to, residual=tc, out=tc, groups=hb, weight_img_rows=c)
+            else:
+                q = ops.linear(ops.layernorm(tc, s.lnt_g, s.lnt_b), s.w_tq)
+                kc = kv[hb * ctx_len:, s.kv_off: s.kv_off + c]
+                vc = kv[hb * ctx_len:, s.kv_off + c: s.kv_off + 2 * c]
+                a = ops.xattn_small_l(q, kc, vc, hb, n, ctx_len, s.heads, 0.125)
+                ops.linear(a, s.w_to, s.b_to, residual=tc, out=tc)
             g = ops.linear(ops.layernorm(t, s.ln3_g, s.ln3_b), s.w_ff1, s.b_ff1, act=ops.UDT_ACT_GEGLU)
             t = ops.linear(g, s.w_ff2, s.b_ff2, residual=t)
             out = ops.linear(t, s.w_out, s.b_out, residual=x.view(nb * n, c))
