@@ -161,10 +161,26 @@ __global__ void __launch_bounds__(256) softmax_groups_kernel(const __half* __res
   const __half* x = in + static_cast<size_t>(row) * ld + g * L;
   float v[16];
   float mx = -INFINITY;
+  const bool vec = (L == 12) && ((ld & 3) == 0);     // 12 tokens = three 8-byte words (consecutive threads: consecutive words)
+  if (vec) {
+    const uint2* x2 = reinterpret_cast<const uint2*>(x);
 #pragma unroll
-  for (int l = 0; l < 16; ++l) {
-    v[l] = (l < L) ? __half2float(x[l]) : -INFINITY;
-    mx = fmaxf(mx, v[l]);
+    for (int w = 0; w < 3; ++w) {
+      const uint2 t = x2[w];
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+      v[4 * w] = a.x; v[4 * w + 1] = a.y; v[4 * w + 2] = b.x; v[4 * w + 3] = b.y;
+    }
+#pragma unroll
+    for (int l = 12; l < 16; ++l) v[l] = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < 12; ++l) mx = fmaxf(mx, v[l]);
+  } else {
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      v[l] = (l < L) ? __half2float(x[l]) : -INFINITY;
+      mx = fmaxf(mx, v[l]);
+    }
   }
   float sum = 0.0f;
   if (L > 1) {
@@ -180,9 +196,15 @@ __global__ void __launch_bounds__(256) softmax_groups_kernel(const __half* __res
     v[0] = 1.0f / (1.0f + __expf(-v[0]));   // sigmoid on a single token (attention.py:159-162)
   }
   __half* y = out + static_cast<size_t>(row) * ld + g * L;
+  if (vec) {
+    uint2* y2 = reinterpret_cast<uint2*>(y);
 #pragma unroll
-  for (int l = 0; l < 16; ++l)
-    if (l < L) y[l] = __float2half_rn(v[l]);
+    for (int w = 0; w < 3; ++w) y2[w] = make_uint2(pack_half2(v[4 * w], v[4 * w + 1]), pack_half2(v[4 * w + 2], v[4 * w + 3]));
+  } else {
+#pragma unroll
+    for (int l = 0; l < 16; ++l)
+      if (l < L) y[l] = __float2half_rn(v[l]);
+  }
   if (probs != nullptr) {
     const int img = row / N, n = row - img * N;
     float* pr = probs + ((static_cast<size_t>(img) * groups + g) * N + n) * L;
