@@ -90,6 +90,21 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Cluster barrier without memory ordering (no MEMBAR.ALL.GPU): enough when the barrier only orders control flow — e.g.
+// "the peer's mbarriers are initialised" (with fence.mbarrier_init) or "the peer no longer touches my shared memory".
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  cluster_arrive_relaxed();
+  cluster_wait();
+}
+// asynchronous 16-byte store into the shared memory of a CTA of the cluster; the bytes are counted on the mbarrier at
+// `bar_cluster_addr` (same CTA as the destination), whose waiters see the data without any fence
+__device__ __forceinline__ void st_async_f64x2(uint32_t dst_cluster_addr, double a, double b, uint32_t bar_cluster_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(dst_cluster_addr),
+               "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(bar_cluster_addr)
+               : "memory");
+}
 // shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -111,6 +126,18 @@ __device__ __forceinline__ double ld_shared_cluster_f64(uint32_t cluster_addr) {
 // prologue early.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Same, with a short sleep between polls: for roles that wait long and are not latency critical (producers waiting for a
+// free stage in an epilogue-bound kernel) — a hot spin loop costs the epilogue warps of the same SM sub-partition issue slots.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+    if (++spins > UDT_SPIN_LIMIT) {
+      asm volatile("trap;");
+    }
+  }
+}
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

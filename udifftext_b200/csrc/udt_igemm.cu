@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
     if (kPair) tmem_alloc_pair<kTmemCols>(tmem_slot); else tmem_alloc<kTmemCols>(tmem_slot);
   }
   tc_fence_before();
-  if (kPair) cluster_sync_all(); else __syncthreads();   // peer barriers must be initialised before remote arrives
+  if (kPair) cluster_sync_relaxed(); else __syncthreads();   // peer barriers must be initialised (fence.mbarrier_init) before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();     // PDL: everything above overlapped the previous kernel; its results are needed from here on
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             const int dx = (taps == 9) ? (t % 3 - p.seg_pad[s]) : (taps == 4 ? ((t & 1) - (p.seg_pad[s] & 1)) : 0);
             for (int c = 0; c < kc; ++c, ++kstep) {
               if (kstep < wi.k0 || kstep >= wi.k1) continue;   // another split's K range
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_wait_backoff(&empty_bar[stage], phase ^ 1u);
               if (issuer) {
                 if (kPair) {
                   // both CTAs' boxes complete on the leader's barrier, which expects the bytes of the whole pair
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
         int n_row = (wi.tile - fast_div(wi.tile, p.mg_n, p.tiles_n) * p.tiles_n) * p.BN + rank * b_rows;
         if (p.b_img_rows > 0) n_row += decode_tile<kPair>(p, wi.tile, rank).n0 * p.b_img_rows;   // this tile's image
         for (int k = wi.k0; k < wi.k1; ++k) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1u);
           if (issuer) {
             if (kPair) {
               if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(b_bytes));
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       int iter = 0;
       for (int wk = tile0; wk < p.num_tiles; wk += tile_step, ++iter) {
         const WorkItem wi = decode_work(p, wk);
-        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        mbar_wait_backoff(&tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
         for (int k = wi.k0; k < wi.k1; ++k) {
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
   }
 
   tc_fence_before();
-  if (kPair) cluster_sync_all(); else __syncthreads();   // the peer may still read our operands / signal our barriers
+  if (kPair) cluster_sync_relaxed(); else __syncthreads();   // the peer may still read our operands / signal our barriers
   if (kTraceBuild && p.trace != nullptr && threadIdx.x == 0) {
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 1] = globaltimer_ns();
     p.trace[static_cast<size_t>(blockIdx.x) * kTraceStride + 3] = static_cast<unsigned long long>(clock64());

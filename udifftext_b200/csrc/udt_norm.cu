@@ -231,7 +231,8 @@ constexpr int kGn1Threads = 512;
 __global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a) {
   griddep_launch();
   extern __shared__ __align__(16) uint8_t gsm[];
-  __shared__ double s_part[kGnMaxGroups][2];
+  __shared__ __align__(16) double s_recv[8][kGnMaxGroups][2];   // per-group partial sums received from every rank
+  __shared__ uint64_t s_xbar;
   __shared__ float s_mean[kGnMaxGroups];
   __shared__ float s_rstd[kGnMaxGroups];
   const int n = blockIdx.y;
@@ -255,11 +256,16 @@ __global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a)
   __shared__ uint64_t s_bar;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
+    mbar_init(&s_xbar, 1);
     fence_mbar_init();
   }
   __syncthreads();
+  cluster_arrive_relaxed();   // "my exchange barrier exists"; waited for just before the first remote store
   griddep_wait();
-  if (threadIdx.x == 0) mbar_expect_tx(&s_bar, static_cast<uint32_t>(nrows) * static_cast<uint32_t>(a.C) * 2u);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&s_bar, static_cast<uint32_t>(nrows) * static_cast<uint32_t>(a.C) * 2u);
+    mbar_expect_tx(&s_xbar, static_cast<uint32_t>(S) * static_cast<uint32_t>(a.groups) * 16u);
+  }
   for (int row = threadIdx.x; row < nrows; row += kGn1Threads) {
     uint8_t* dst = gsm + static_cast<size_t>(row) * a.C * 2;
     bulk_load_1d(dst, a.x0 + (pix0 + row) * a.C0, static_cast<uint32_t>(a.C0) * 2u, &s_bar);
@@ -282,19 +288,22 @@ __global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a)
     const int g = threadIdx.x >> 4, j = threadIdx.x & 15;   // 16 lanes per group (512 threads, <= 32 groups)
     double ds, dq;
     gn_group_fold(ps, pq, rpi, a.C, cpg, min(g, a.groups - 1), j, 16, ds, dq);
+    cluster_wait();                                  // every CTA of the cluster has initialised its exchange barrier
     if (j == 0 && g < a.groups) {
-      s_part[g][0] = ds;
-      s_part[g][1] = dq;
+      // push this CTA's partial sums of group g to every CTA of the cluster (itself included): asynchronous 16-byte
+      // stores counted on the receiver's mbarrier — no cluster-wide memory fence, no second cluster barrier
+      const uint32_t dst = smem_u32(&s_recv[rank][g][0]);
+      const uint32_t bar = smem_u32(&s_xbar);
+      for (int rk = 0; rk < S; ++rk)
+        st_async_f64x2(mapa_u32(dst, static_cast<uint32_t>(rk)), ds, dq, mapa_u32(bar, static_cast<uint32_t>(rk)));
     }
   }
-  cluster_sync_all();
+  mbar_wait(&s_xbar, 0);                             // all S contributions have landed in s_recv
   if (threadIdx.x < a.groups) {
-    const uint32_t base = smem_u32(&s_part[threadIdx.x][0]);
     double ds = 0.0, dq = 0.0;
     for (int rk = 0; rk < S; ++rk) {               // fixed order over the cluster: deterministic
-      const uint32_t ra = mapa_u32(base, static_cast<uint32_t>(rk));
-      ds += ld_shared_cluster_f64(ra);
-      dq += ld_shared_cluster_f64(ra + 8);
+      ds += s_recv[rk][threadIdx.x][0];
+      dq += s_recv[rk][threadIdx.x][1];
     }
     const double cnt = static_cast<double>(a.HW) * cpg;
     const double mean = ds / cnt;
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a)
     s_mean[threadIdx.x] = static_cast<float>(mean);
     s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
   }
-  cluster_sync_all();   // remote reads of s_part are complete before any CTA may exit; also publishes s_mean / s_rstd
+  __syncthreads();      // publishes s_mean / s_rstd (peers only ever WRITE to this CTA, and all of those writes have landed)
   if (act) {
     float A[8], B[8];
 #pragma unroll
