@@ -226,12 +226,13 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
 }
 
 constexpr int kGn1Threads = 512;
+constexpr int kGn1MaxCluster = 16;      // 16 = non-portable cluster size (one cluster per GPC); 8 if the device refuses it
 
 // one-pass GroupNorm: grid (S, NB), cluster (S, 1, 1); CTA `rank` of a cluster owns rows [rank*R, rank*R + R) of sample n
 __global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a) {
   griddep_launch();
   extern __shared__ __align__(16) uint8_t gsm[];
-  __shared__ __align__(16) double s_recv[8][kGnMaxGroups][2];   // per-group partial sums received from every rank
+  __shared__ __align__(16) double s_recv[kGn1MaxCluster][kGnMaxGroups][2];   // per-group partial sums received from every rank
   __shared__ uint64_t s_xbar;
   __shared__ float s_mean[kGnMaxGroups];
   __shared__ float s_rstd[kGnMaxGroups];
@@ -346,13 +347,13 @@ __global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a)
   }
 }
 
-constexpr int kGn1SlabBudget = 184 * 1024;   // + <= 32 KB of partial sums + static smem < 227 KB
+constexpr int kGn1SlabBudget = 176 * 1024;   // + <= 32 KB of partial sums (<= 208 KB dynamic) + ~9 KB static < 227 KB
 
 // cluster size of the one-pass schedule for this problem, 0 = use the two-pass schedule
-inline int gn_onepass_cluster(int NB, int HW, int C) {
+inline int gn_onepass_cluster(int NB, int HW, int C, int max_cluster) {
   if (C / 8 > kGn1Threads) return 0;
   int s_fit = 0;
-  for (int s = 1; s <= 8; s <<= 1) {
+  for (int s = 1; s <= max_cluster; s <<= 1) {
     const long slab = static_cast<long>((HW + s - 1) / s) * C * 2;
     if (slab <= kGn1SlabBudget) {
       s_fit = s;
@@ -361,7 +362,7 @@ inline int gn_onepass_cluster(int NB, int HW, int C) {
   }
   if (s_fit == 0) return 0;
   int s = s_fit;
-  while (s < 8 && NB * s < 96 && 2 * s <= HW) s <<= 1;   // spread small problems over more SMs
+  while (s < 8 && NB * s < 96 && 2 * s <= HW) s <<= 1;   // spread small problems over more SMs (portable sizes only)
   return s;
 }
 
@@ -582,14 +583,39 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
     const char* e = getenv("UDT_GN_ONEPASS");
     return e == nullptr || atoi(e) != 0;
   }();
-  const int S = onepass_ok ? gn_onepass_cluster(NB, HW, C) : 0;
-  if (S > 0) {
-    static bool attr1_set = false;
-    if (!attr1_set) {
-      cudaError_t e = cudaFuncSetAttribute(gn_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-      if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(gn one-pass smem): %s", cudaGetErrorString(e));
-      attr1_set = true;
+  // largest usable cluster: 16 CTAs (non-portable size) when the device can co-schedule such a cluster with the
+  // kernel's full shared-memory footprint, else the portable 8
+  static int max_cluster = 0;
+  if (max_cluster == 0) {
+    cudaError_t e = cudaFuncSetAttribute(gn_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(gn one-pass smem): %s", cudaGetErrorString(e));
+    max_cluster = 8;
+    static const bool big_ok = [] {
+      // opt-in: measured SLOWER than the two-pass schedule on B200 (8 co-resident clusters of 16 CTAs pull a 2.6 MB sample
+      // at single-SM rates: 64x64x320 28 us vs 19 us), kept for experiments
+      const char* e2 = getenv("UDT_GN_CLUSTER16");
+      return e2 != nullptr && atoi(e2) != 0;
+    }();
+    if (big_ok && cudaFuncSetAttribute(gn_onepass_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(16, 1, 1);
+      q.blockDim = dim3(kGn1Threads, 1, 1);
+      q.dynamicSmemBytes = 208 * 1024;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 16;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, gn_onepass_kernel, &q) == cudaSuccess && nclusters >= 4) max_cluster = 16;
     }
+    (void)cudaGetLastError();
+  }
+  const int S = onepass_ok ? gn_onepass_cluster(NB, HW, C, max_cluster) : 0;
+  if (S > 0) {
     a.rows_per_cta = (HW + S - 1) / S;
     a.chunks = S;
     const int rpi1 = kGn1Threads / (C / 8);
