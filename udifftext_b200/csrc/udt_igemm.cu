@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) {
             const float x = __uint_as_float(v[j]) + my_bias[c0 + j];
             const float gt = __uint_as_float(vg[j]) + my_bias[p.BN / 2 + c0 + j];
-            f[j] = x * gelu_erf_f(gt);
+            f[j] = x * gelu_erf_fast(gt);
           }
         } else {
           if (!UDT_DBG(p, 8)) tmem_ld_wait_dep(v);   // this chunk's accumulators have landed in v[]
