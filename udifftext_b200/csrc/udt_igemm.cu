@@ -62,6 +62,7 @@ struct IGemmParams {
   int32_t nseg, ksteps;
   int32_t W, H, NB;
   int32_t bw, bh, bn;
+  int32_t lbw, lbh;      // log2(bw), log2(bh): the spatial tile sides are powers of two
   int32_t tiles_w, tiles_h, tiles_nb, tiles_n, num_tiles;
   uint32_t mg_n, mg_w, mg_h;   // fast_div magic numbers of tiles_n, tiles_w, tiles_h
   // split-K (small-M, weight-streaming problems): work item = (tile, split); split s accumulates K steps
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
   // block and the operand ring
   const bool has_res_stage = kStaged && !kGeglu && p.residual != nullptr;
   const int group_bytes = (p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes;
-  const int epi_bytes = kStaged ? p.egroups * group_bytes : 0;
+  const int epi_bytes = kStaged ? p.egroups * group_bytes : (p.ksplit > 1 ? 8 * 4096 : 0);   // split-K: transpose scratch
 
   const int b_rows = kPair ? p.BN / 2 : p.BN;          // weight rows this CTA stages per K step
   const int b_bytes = b_rows * kBlockK * 2;
@@ -320,6 +321,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           const int kc = p.seg_kc[s];
           const int sw0 = tc.w0 * p.seg_stride[s], sh0 = tc.h0 * p.seg_stride[s];
           for (int t = 0; t < taps; ++t) {
+            if (kstep >= wi.k1) break;                       // split-K: past this work item's K range
+            if (kstep + kc <= wi.k0) {                       // split-K: whole tap before the range
+              kstep += kc;
+              continue;
+            }
             // 3x3 window: (ky, kx) - pad;  2x2 window (one phase of a fused nearest-2x upsample conv): pad = 2*pad_y + pad_x
             const int dy = (taps == 9) ? (t / 3 - p.seg_pad[s]) : (taps == 4 ? ((t >> 1) - (p.seg_pad[s] >> 1)) : 0);
             const int dx = (taps == 9) ? (t % 3 - p.seg_pad[s]) : (taps == 4 ? ((t & 1) - (p.seg_pad[s] & 1)) : 0);
@@ -668,6 +674,62 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
       if (as == 0) aphase ^= 1u;
     }
     if (issuer && active) tma_store_wait_all<0>();   // all output slabs written before the CTA retires
+  } else if (p.ksplit > 1) {
+    // ------------------------------------------------------------------ split-K partial tiles (warps 2..9)
+    // raw fp32 accumulators -> workspace.  tcgen05.ld hands every thread one ROW (32 columns = 128 B); written as is, one
+    // store instruction would touch 32 different rows.  Each warp therefore transposes its 32x32 block through a 4 KB
+    // XOR-swizzled shared-memory scratch so that eight lanes write one row's 128 bytes (4 full lines per instruction).
+    const int quarter = warp & 3;
+    const int eg = (warp - 2) >> 2;
+    float* scratch = reinterpret_cast<float*>(base + kCtrlBytes + (warp - 2) * 4096);
+    const int nch = p.BN / kChunkCols;
+    const int sub = lane >> 3, cj = lane & 7;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int wk = tile0; wk < p.num_tiles; wk += tile_step) {
+      const WorkItem wi = decode_work(p, wk);
+      const TileCoord tc = decode_tile<kPair>(p, wi.tile, rank);
+      long long moff[8];
+      bool ok[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {             // the 8 rows of this warp's block that this lane stores
+        const int r = quarter * 32 + 4 * i + sub;
+        const int w = tc.w0 + (r & (p.bw - 1));
+        const int h = tc.h0 + ((r >> p.lbw) & (p.bh - 1));
+        const int n = tc.n0 + (r >> (p.lbw + p.lbh));
+        ok[i] = (w < p.W) && (h < p.H) && (n < p.NB);
+        moff[i] = ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.ldo;
+      }
+      float* outp = reinterpret_cast<float*>(p.out) + static_cast<long long>(wi.split) * p.split_stride;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
+      for (int c = eg; c < nch; c += 2) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * kChunkCols, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(scratch + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = tc.n_blk * p.BN + c * kChunkCols + cj * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + sub;
+          const uint4 t = *reinterpret_cast<const uint4*>(scratch + rl * 32 + ((cj ^ (rl & 7)) << 2));
+          if (ok[i] && col + 4 <= p.N_out) *reinterpret_cast<uint4*>(outp + moff[i] + col) = t;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0)); else mbar_arrive(&tmem_empty[as]);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
   } else if (warp >= 6) {
     // ------------------------------------------------------------------ direct mode: warps 6..9 only hand-shake
     int as = 0;
@@ -959,6 +1021,10 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
       }
     }
   }
+  p.lbw = 0;
+  while ((1 << p.lbw) < p.bw) ++p.lbw;
+  p.lbh = 0;
+  while ((1 << p.lbh) < p.bh) ++p.lbh;
   p.W = W;
   p.H = H;
   p.NB = NB;
@@ -1099,6 +1165,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
       epi_bytes = (p.out_bufs + p.res_bufs) * kChunkBytes + kBiasBytes;
     }
   }
+  if (ksplit > 1) epi_bytes = 8 * 4096;   // per-warp transpose scratch of the split-K partial-tile stores
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   int stages = (kSmemBudget - kCtrlBytes - 1024 - epi_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
