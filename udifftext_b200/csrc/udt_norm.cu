@@ -32,6 +32,7 @@ struct GnArgs {
   const float* gamma;
   const float* beta;
   double* partial;  // [NB, groups, chunks, 2] per-CTA partial (sum, sum of squares)
+  double* folded;   // [NB, groups, 2] (sum, sum of squares) folded by gn_fold_kernel when there are many chunks, else NULL
   int C0, C1, C, NB, HW, groups, rows_per_cta, chunks, silu;
   float eps;
 };
@@ -100,10 +101,18 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
   __syncthreads();
   griddep_wait();     // PDL: wait for the producers of our inputs
   if (threadIdx.x == 0) mbar_expect_tx(&s_bar, static_cast<uint32_t>(nrows) * static_cast<uint32_t>(a.C) * 2u);
-  for (int row = threadIdx.x; row < nrows; row += blockDim.x) {
-    uint8_t* dst = gsm2 + static_cast<size_t>(row) * a.C * 2;
-    bulk_load_1d(dst, a.x0 + (pix0 + row) * a.C0, static_cast<uint32_t>(a.C0) * 2u, &s_bar);
-    if (a.C1 > 0) bulk_load_1d(dst + a.C0 * 2, a.x1 + (pix0 + row) * a.C1, static_cast<uint32_t>(a.C1) * 2u, &s_bar);
+  if (a.C1 == 0) {
+    // single source: the slab is one contiguous range of global memory -> a few large bulk copies (16 KB pieces)
+    const uint32_t total = static_cast<uint32_t>(nrows) * static_cast<uint32_t>(a.C) * 2u;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.x0 + pix0 * a.C0);
+    for (uint32_t off = threadIdx.x * 16384u; off < total; off += blockDim.x * 16384u)
+      bulk_load_1d(gsm2 + off, src + off, min(16384u, total - off), &s_bar);
+  } else {
+    for (int row = threadIdx.x; row < nrows; row += blockDim.x) {
+      uint8_t* dst = gsm2 + static_cast<size_t>(row) * a.C * 2;
+      bulk_load_1d(dst, a.x0 + (pix0 + row) * a.C0, static_cast<uint32_t>(a.C0) * 2u, &s_bar);
+      bulk_load_1d(dst + a.C0 * 2, a.x1 + (pix0 + row) * a.C1, static_cast<uint32_t>(a.C1) * 2u, &s_bar);
+    }
   }
   mbar_wait(&s_bar, 0);
   const int r = threadIdx.x / vcols;
@@ -134,6 +143,35 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnArgs a) {
   }
 }
 
+// large tensors (VAE resolutions: thousands of chunks per image): fold the per-CTA partials ONCE, in a fixed order, instead
+// of in every CTA of the apply pass.  grid (groups, NB), 256 threads.
+__global__ void __launch_bounds__(256) gn_fold_kernel(const GnArgs a) {
+  griddep_launch();
+  griddep_wait();
+  __shared__ double s_s[256], s_q[256];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const double* st = a.partial + (static_cast<size_t>(n) * a.groups + g) * a.chunks * 2;
+  double ds = 0.0, dq = 0.0;
+  for (int c = threadIdx.x; c < a.chunks; c += 256) {
+    ds += st[2 * c];
+    dq += st[2 * c + 1];
+  }
+  s_s[threadIdx.x] = ds;
+  s_q[threadIdx.x] = dq;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_s[threadIdx.x] += s_s[threadIdx.x + o];
+      s_q[threadIdx.x] += s_q[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.folded[(static_cast<size_t>(n) * a.groups + g) * 2] = s_s[0];
+    a.folded[(static_cast<size_t>(n) * a.groups + g) * 2 + 1] = s_q[0];
+  }
+}
+
 // pass 2: fold the partials in a fixed order, then y = x * A[c] + B[c] (+SiLU); every thread owns fixed 8-channel
 // vectors (its A / B coefficients live in registers) and walks the CTA's rows with 4 loads in flight
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
@@ -147,11 +185,18 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
   {
     const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
     if (g < a.groups) {
-      const double* st = a.partial + (static_cast<size_t>(n) * a.groups + g) * a.chunks * 2;
       double ds = 0.0, dq = 0.0;
-      for (int c = j; c < a.chunks; c += 8) {
-        ds += st[2 * c];
-        dq += st[2 * c + 1];
+      if (a.folded != nullptr) {            // many chunks: gn_fold_kernel has already summed them
+        if (j == 0) {
+          ds = a.folded[(static_cast<size_t>(n) * a.groups + g) * 2];
+          dq = a.folded[(static_cast<size_t>(n) * a.groups + g) * 2 + 1];
+        }
+      } else {
+        const double* st = a.partial + (static_cast<size_t>(n) * a.groups + g) * a.chunks * 2;
+        for (int c = j; c < a.chunks; c += 8) {
+          ds += st[2 * c];
+          dq += st[2 * c + 1];
+        }
       }
       s_red[g][j][0] = ds;
       s_red[g][j][1] = dq;
@@ -548,7 +593,7 @@ extern "C" int64_t udt_groupnorm_ws_bytes(int32_t NB, int32_t HW, int32_t C, int
   if (NB < 1 || HW < 1 || C < 8 || groups < 1) return 0;
   const int rows = gn_rows_per_cta(C, HW);
   const int chunks = (HW + rows - 1) / rows;
-  return static_cast<int64_t>(NB) * groups * chunks * 2 * static_cast<int64_t>(sizeof(double));
+  return static_cast<int64_t>(NB) * groups * (chunks + 1) * 2 * static_cast<int64_t>(sizeof(double));   // + folded sums
 }
 
 extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, int32_t C1, void* y, int32_t NB,
@@ -571,6 +616,7 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
   a.gamma = gamma;
   a.beta = beta;
   a.partial = reinterpret_cast<double*>(stats_ws);
+  a.folded = nullptr;
   a.C0 = C0;
   a.C1 = C1;
   a.C = C;
@@ -650,7 +696,12 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
     attr_set = true;
   }
   dim3 grid(a.chunks, NB);
+  a.folded = nullptr;
   udt_host::launch_pdl(gn_stats_kernel, dim3(grid), dim3(kGnThreads), smem_stats, st, a);
+  if (a.chunks > 64) {
+    a.folded = a.partial + static_cast<size_t>(NB) * groups * a.chunks * 2;
+    udt_host::launch_pdl(gn_fold_kernel, dim3(groups, NB), dim3(256), 0, st, a);
+  }
   udt_host::launch_pdl(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0, st, a);
   return check_launch("udt_groupnorm_nhwc");
 }

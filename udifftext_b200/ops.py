@@ -49,20 +49,10 @@ def _invoke(name: str, *args, shape=None) -> None:
     _lib.check(rc, name)
 
 
-def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
-    """Live per-entry-point device time of ONE sampler step (udt_cfg_pack -> UNet -> udt_cfg_euler_step).
-
-    The step is executed once eagerly while every C-ABI call (function, arguments) is recorded; each distinct
-    (entry point, problem shape) is then replayed `reps` times back to back inside a CUDA graph on the launching
-    stream and timed with CUDA events around the replay (no host launch cost, no per-call event overhead, programmatic
-    dependent launch active exactly as in the product's step graph); a shape's time is multiplied by its call count.
-    Also returns the duration of the whole step as a CUDA-graph replay.  The runner's state is restored afterwards."""
+def profile_callable(fn, reps: int = 20) -> dict:
+    """device time of every C-ABI call `fn()` makes: the calls are recorded during one eager execution, then each distinct
+    (entry point, problem shape) is replayed `reps` times back to back inside a CUDA graph and timed with CUDA events"""
     global CALL_LOG, SHAPE_LOG
-    x_saved = runner.x.clone()
-    runner.row.copy_(runner.table[0:1])
-    for _ in range(warm):
-        runner._body()
-    torch.cuda.synchronize()
     keep = []                       # keep the logged step's temporaries alive: the recorded raw pointers stay valid
     orig_empty = torch.empty
 
@@ -75,23 +65,23 @@ def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
     shape_log_prev = SHAPE_LOG
     SHAPE_LOG, CALL_LOG = [], []
     try:
-        runner._body()
+        fn()
         torch.cuda.synchronize()
     finally:
         torch.empty = orig_empty
         calls, CALL_LOG, SHAPE_LOG = CALL_LOG, None, shape_log_prev
     groups: dict = {}
-    for name, fn, args, shape in calls:
-        groups.setdefault((name, shape), []).append((fn, args))
+    for name, cfn, args, shape in calls:
+        groups.setdefault((name, shape), []).append((cfn, args))
     acc: dict = {}
     shapes = []
     for (name, shape), lst in groups.items():
-        fn, args = lst[0]
+        cfn, args = lst[0]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             st = torch.cuda.current_stream().cuda_stream
             for _ in range(reps):
-                _lib.check(fn(*args, st), name)
+                _lib.check(cfn(*args, st), name)
         g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -104,6 +94,26 @@ def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
         a["ms"] += ms * len(lst)
         a["calls"] += len(lst)
         shapes.append({"op": name, "shape": [str(v) for v in shape], "calls": len(lst), "us_per_call": 1e3 * ms})
+    shapes.sort(key=lambda r: -r["us_per_call"] * r["calls"])
+    del keep
+    return {"by_op": acc, "by_shape": shapes, "total_ms": sum(a["ms"] for a in acc.values())}
+
+
+def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
+    """Live per-entry-point device time of ONE sampler step (udt_cfg_pack -> UNet -> udt_cfg_euler_step).
+
+    The step is executed once eagerly while every C-ABI call (function, arguments) is recorded; each distinct
+    (entry point, problem shape) is then replayed `reps` times back to back inside a CUDA graph on the launching
+    stream and timed with CUDA events around the replay (no host launch cost, no per-call event overhead, programmatic
+    dependent launch active exactly as in the product's step graph); a shape's time is multiplied by its call count.
+    Also returns the duration of the whole step as a CUDA-graph replay.  The runner's state is restored afterwards."""
+    x_saved = runner.x.clone()
+    runner.row.copy_(runner.table[0:1])
+    for _ in range(warm):
+        runner._body()
+    torch.cuda.synchronize()
+    res = profile_callable(runner._body, reps)
+    acc, shapes = res["by_op"], res["by_shape"]
     total = sum(a["ms"] for a in acc.values())
     step_ms_graph = None
     if runner.graph is not None:
@@ -118,8 +128,6 @@ def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
         torch.cuda.synchronize()
         step_ms_graph = e0.elapsed_time(e1) / 5
     runner.x.copy_(x_saved)
-    del keep
-    shapes.sort(key=lambda r: -r["us_per_call"] * r["calls"])
     return {"by_op": acc, "step_ms_eager_sum": total, "step_ms_graph": step_ms_graph, "by_shape": shapes}
 
 
