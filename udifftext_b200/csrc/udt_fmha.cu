@@ -15,7 +15,11 @@
 //                              key tile the scores are read from TMEM ONCE: exponentials are taken against the current
 //                              reference while the tile maximum is tracked, and only a (rare) violation of the 2^8
 //                              bound replays the tile.  The tcgen05.ld of the next 32 columns flies during the math.
-//                              P_t is written as fp16 into 128B-swizzled shared memory for the PV MMA.
+//                              P_t goes back into TENSOR MEMORY as fp16 pairs over the first 64 columns of its own
+//                              (fully consumed) score buffer and feeds the PV MMA as a TMEM A operand (TS form):
+//                              tcgen05.st is 4x faster than tcgen05.ld, no shared-memory round trip, and the freed
+//                              64 KB of P buffers buy a 4-stage K / V ring (udt_fmha_ts_kernel, +4-5 % over the
+//                              smem-P kernel udt_fmha_kernel, which is kept for A/B runs: UDT_FMHA_TS=0).
 // Replaces xformers.ops.memory_efficient_attention at reference sgm/modules/attention.py:246-248.
 #include "udt_common.cuh"
 #include "udt_host.h"
@@ -58,18 +62,23 @@ constexpr int kOffK = kOffQ + 2 * kTileBytes;
 constexpr int kOffV = kOffK + kKvStages * kTileBytes;
 constexpr int kOffP = kOffV + kKvStages * kTileBytes;
 constexpr int kSmemBytes = kOffP + 2 * kPBytes + 1024;
+// TS variant (P kept in TMEM): no P buffers, a deeper K / V ring instead
+constexpr int kTsKvStages = 4;
+constexpr int kTsOffK = kOffQ + 2 * kTileBytes;
+constexpr int kTsOffV = kTsOffK + kTsKvStages * kTileBytes;
+constexpr int kTsSmemBytes = kTsOffV + kTsKvStages * kTileBytes + 1024;
 
 // cursor over the score computations c = j * ntiles + t (key tile j, query tile t) without integer divisions
 struct CompCursor {
   int c, j, t, stage, kvphase, b, u;   // stage = j % kKvStages, kvphase = (j / kKvStages) & 1, b = c % kSBufs, u = c / kSBufs
   __device__ __forceinline__ void init() { c = j = t = stage = kvphase = b = u = 0; }
-  __device__ __forceinline__ void advance(int ntiles) {
+  __device__ __forceinline__ void advance(int ntiles, int kvstages = kKvStages) {
     ++c;
     if (++b == kSBufs) { b = 0; ++u; }
     if (++t == ntiles) {
       t = 0;
       ++j;
-      if (++stage == kKvStages) { stage = 0; kvphase ^= 1; }
+      if (++stage == kvstages) { stage = 0; kvphase ^= 1; }
     }
   }
 };
@@ -364,6 +373,294 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
   }
 }
 
+__global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_constant__ FmhaParams p) {
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base = smem_raw + (base_addr - raw_addr);
+
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(base + kOffCtrl);
+  uint64_t* kv_full = q_full + 1;            // [kTsKvStages]
+  uint64_t* kv_empty = kv_full + kTsKvStages;  // [kTsKvStages]
+  uint64_t* s_full = kv_empty + kTsKvStages;   // [kSBufs]  scores of a computation are in TMEM
+  uint64_t* s_free = s_full + kSBufs;        // [kSBufs]  the consuming warpgroup has read them
+  uint64_t* p_full = s_free + kSBufs;        // [2]       P_t(j) is in shared memory
+  uint64_t* o_full = p_full + 2;             // [2]       P_t(j) V_j has been accumulated into O_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.z;
+  const int h = blockIdx.y;
+  const int q0 = blockIdx.x * 2 * kTile;                 // first query row (within the batch) of this CTA
+  const int ntiles = (p.Nq - q0 > kTile) ? 2 : 1;        // second query tile present?
+  const int nkv = (p.Nkv + kTile - 1) / kTile;
+  const int ncomp = nkv * ntiles;
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kTsKvStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < kSBufs; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();     // PDL: q / k / v are produced by the previous kernel
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int col = h * kD;
+      mbar_expect_tx(q_full, static_cast<uint32_t>(ntiles * kTileBytes));
+      for (int t = 0; t < ntiles; ++t)
+        tma_load_2d(&p.mapQ, q_full, base + kOffQ + t * kTileBytes, col, b * p.Nq + q0 + t * kTile);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1u);
+        mbar_expect_tx(&kv_full[s], 2u * kTileBytes);
+        tma_load_2d(&p.mapK, &kv_full[s], base + kTsOffK + s * kTileBytes, col, b * p.Nkv + j * kTile);
+        tma_load_2d(&p.mapV, &kv_full[s], base + kTsOffV + s * kTileBytes, col, b * p.Nkv + j * kTile);
+        if (++s == kTsKvStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const bool issuer = elect_one();
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
+    auto issue_s = [&](const CompCursor& k) {
+      if (k.t == 0) mbar_wait(&kv_full[k.stage], static_cast<uint32_t>(k.kvphase));
+      // (buffer reuse needs no barrier: P of computation c lives in S buffer c % 3, and S(c+3) is issued after P V(c) by this
+      //  same thread — the tensor pipe executes them in order)
+      tc_fence_after();
+      if (issuer) {
+        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + k.t * kTileBytes);
+        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kTsOffK + k.stage * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk)
+          umma_f16_ss(tmem_base + kColS + k.b * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
+                      idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&s_full[k.b]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    CompCursor ks, kp;   // score cursor runs kSBufs computations ahead of the PV cursor
+    ks.init();
+    kp.init();
+    for (int i = 0; i < kSBufs && ks.c < ncomp; ++i) {
+      issue_s(ks);
+      ks.advance(ntiles, kTsKvStages);
+    }
+    for (; kp.c < ncomp; kp.advance(ntiles, kTsKvStages)) {
+      mbar_wait(&p_full[kp.t], static_cast<uint32_t>(kp.j & 1));   // P_t(j) is in smem, S of this computation is released
+      tc_fence_after();
+      if (issuer) {
+        const uint32_t v_addr = base_addr + kTsOffV + kp.stage * kTileBytes;
+        const uint32_t p_tmem = tmem_base + kColS + kp.b * 128;   // P (fp16 pairs) aliases the first 64 columns of its S buffer
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk) {
+          const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
+          umma_f16_ts(tmem_base + kColO + kp.t * 64, p_tmem + kk * 8, dv, idesc_o, (kp.j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[kp.t]);
+        if (kp.t == ntiles - 1) umma_commit(&kv_empty[kp.stage]);   // last reader of this K/V stage
+      }
+      __syncwarp();
+      if (ks.c < ncomp) {
+        issue_s(ks);
+        ks.advance(ntiles, kTsKvStages);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int t = warp >> 2;  // query tile handled by this warpgroup
+    if (t < ntiles) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t o_addr = tmem_base + lane_base + kColO + t * 64;
+      const float sl2 = p.scale_log2;
+      float m_ref = -INFINITY, l = 0.0f;
+      int sb = t, su = 0;   // S buffer / use count of this warpgroup's next computation (c = j * ntiles + t)
+
+      // rescale the running output (and row sum) when the reference maximum moves; O_t must be stable
+      auto rescale = [&](bool need, float m_tile, int j) {
+        const float m_new = need ? m_tile : m_ref;
+        const float alpha = need ? ex2_approx(m_ref - m_new) : 1.0f;  // m_ref = -inf on the first tile -> 0
+        l *= alpha;
+        if (j > 0) {
+          mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(o_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(o_addr + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+        m_ref = m_new;
+      };
+
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&s_full[sb], static_cast<uint32_t>(su & 1));
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_base + kColS + sb * 128;
+        const int key_lim = p.Nkv - j * kTile;  // keys >= key_lim of this tile are padding (only on the last tile)
+        const bool partial = key_lim < kTile;
+        float rowsum = 0.0f;
+        bool replay = (j == 0) || partial;      // first / ragged tile: maximum first, then the exponentials
+        // 32 probabilities (keys [32*ch, 32*ch+32) of this tile) -> fp16 -> this row's swizzled slots of the P buffer;
+        // the stores interleave with the exponentials of the following chunk
+        uint32_t pall[64];                      // the tile's probabilities, fp16 pairs (key 2i | key 2i+1)
+        auto store_chunk = [&](const uint32_t (&pk)[16], int ch) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pall[ch * 16 + i] = pk[i];
+        };
+        if (!replay) {
+          // ---- single pass: exponentials against the current reference, written to the P buffer right away.  No
+          // maximum is tracked: every probability is bounded by 2^8 unless the tile's row sum exceeds 2^8, so a row sum
+          // above that bound (rare: the reference would have to be stale by almost the whole lazy margin) sends the tile
+          // through the two-pass path, which overwrites the optimistic P (nobody reads it before p_full).
+          uint32_t va[32], vb[32];
+          auto exp_chunk = [&](const uint32_t (&vv)[32], int ch) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = fmaf(__uint_as_float(vv[i]), sl2, -m_ref);
+              float p1 = fmaf(__uint_as_float(vv[i + 1]), sl2, -m_ref);
+              if (!UDT_FDBG(1)) {
+                p0 = ex2_approx(p0);
+                p1 = ex2_approx(p1);
+              }
+              rowsum += p0 + p1;
+              pk[i >> 1] = pack_half2(p0, p1);
+            }
+            if (!UDT_FDBG(2)) store_chunk(pk, ch);
+          };
+          tmem_ld32(s_addr, va);
+          tmem_ld_wait_dep(va);
+          tmem_ld32(s_addr + 32, vb);      // the next 32 columns fly during the math
+          exp_chunk(va, 0);
+          tmem_ld_wait_dep(vb);
+          tmem_ld32(s_addr + 64, va);
+          exp_chunk(vb, 1);
+          tmem_ld_wait_dep(va);
+          tmem_ld32(s_addr + 96, vb);
+          exp_chunk(va, 2);
+          tmem_ld_wait_dep(vb);
+          exp_chunk(vb, 3);
+          replay = __any_sync(0xffffffffu, !(rowsum <= 256.0f)) && !UDT_FDBG(3);   // also catches inf / nan
+        }
+        if (replay) {
+          // ---- two passes: row maximum of the raw scores, reference update (+ O rescale), exponentials
+          uint32_t v[32];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!partial || ch * 32 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          const float m_tile = mx * sl2;
+          const bool need = m_tile > m_ref + kLazyThreshold;
+          if (__any_sync(0xffffffffu, need)) rescale(need, m_tile, j);
+          rowsum = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
+              if (partial) {
+                const int k0 = ch * 32 + i;
+                if (k0 >= key_lim) p0 = 0.0f;
+                if (k0 + 1 >= key_lim) p1 = 0.0f;
+              }
+              rowsum += p0 + p1;
+              pk[i >> 1] = pack_half2(p0, p1);
+            }
+            store_chunk(pk, ch);
+          }
+        }
+        l += rowsum;
+        // ---- P -> TMEM, over the first 64 columns of the (fully consumed) score buffer: the PV MMA reads it as its A operand
+        {
+          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pall[0]);
+          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pall[32]);
+          tmem_st32(s_addr, lo);
+          tmem_st32(s_addr + 32, hi);
+          tmem_st_wait();
+        }
+        // observe every o_full phase (the wait is almost always already satisfied: P_t V_{j-1} ran during this tile's
+        // exponentials); a parity wait that skipped phases would be ambiguous in rescale() and at the end
+        if (j > 0) mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_before();         // TMEM reads of S / writes of P, O_t ordered before the arrive
+        mbar_arrive(&p_full[t]);
+        sb += ntiles;
+        if (sb >= kSBufs) { sb -= kSBufs; ++su; }
+      }
+      mbar_wait(&o_full[t], static_cast<uint32_t>((nkv - 1) & 1));
+      tc_fence_after();
+      const int qrow = q0 + t * kTile + row;
+      const float inv = 1.0f / l;
+      uint4* o4 = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.Nq + min(qrow, p.Nq - 1)) * p.ldo + h * kD);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(o_addr + c * 32, v);
+        tmem_ld_wait();
+        if (qrow < p.Nq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 ov;
+            ov.x = pack_half2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+            ov.y = pack_half2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+            ov.z = pack_half2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+            ov.w = pack_half2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+            o4[c * 4 + g] = ov;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+
 }  // namespace
 
 extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t Nq, int32_t Nkv,
@@ -396,6 +693,18 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   static const int dbg = [] { const char* e = getenv("UDT_FMHA_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
   dim3 grid((Nq + 2 * kTile - 1) / (2 * kTile), heads, B);
+  // P kept in TMEM (TS-form PV MMA) is the production schedule; UDT_FMHA_TS=0 selects the smem-P kernel for A/B measurements
+  static const int use_ts = [] { const char* e = getenv("UDT_FMHA_TS"); return e ? atoi(e) : 1; }();
+  if (use_ts) {
+    static bool ts_attr = false;
+    if (!ts_attr) {
+      cudaError_t e = cudaFuncSetAttribute(udt_fmha_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
+      if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha ts smem): %s", cudaGetErrorString(e));
+      ts_attr = true;
+    }
+    udt_host::launch_pdl(udt_fmha_ts_kernel, dim3(grid), dim3(kThreads), kTsSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
+    return check_launch("udt_fmha_fwd (ts)");
+  }
   udt_host::launch_pdl(udt_fmha_kernel, dim3(grid), dim3(kThreads), kSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("udt_fmha_fwd");
 }
