@@ -53,7 +53,29 @@ struct FmhaParams {
   int32_t Nq, Nkv, heads, ldo;
   float scale_log2;
   int32_t debug;   // UDT_FMHA_DEBUG experiment switches (tuning only; 0 in production)
+  int32_t pairs_per_bh;   // CTAs [0, pairs_full) own a PAIR of query tiles (256 rows) of one (batch, head), numbered
+  int32_t pairs_full;     // (b * heads + h) * pairs_per_bh + pair; the CTAs after them own ONE tile of the remaining pairs
 };
+
+// Work of this CTA.  The grid is linear: whole waves of tile pairs first, then — when the last, partial wave would leave
+// more than half of the SMs idle — its pairs as twice as many single-tile CTAs (a single-tile CTA has the exp pipe and
+// the TMEM read port to itself and finishes in ~0.55 of a pair's time, so the tail wave shrinks accordingly).
+__device__ __forceinline__ bool fmha_work(const FmhaParams& p, int& b, int& h, int& q0, int& ntiles) {
+  const int L = static_cast<int>(blockIdx.x);
+  int pair = L, half = 0;
+  const bool single = L >= p.pairs_full;
+  if (single) {
+    const int s = L - p.pairs_full;
+    pair = p.pairs_full + (s >> 1);
+    half = s & 1;
+  }
+  const int bh = pair / p.pairs_per_bh;
+  b = bh / p.heads;
+  h = bh - b * p.heads;
+  q0 = (pair - bh * p.pairs_per_bh) * 2 * kTile + half * kTile;   // first query row (within the batch) of this CTA
+  ntiles = (!single && p.Nq - q0 > kTile) ? 2 : 1;                // second query tile present?
+  return q0 < p.Nq;
+}
 
 // smem layout (offsets from the 1024-aligned base)
 constexpr int kOffCtrl = 0;
@@ -101,10 +123,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.z;
-  const int h = blockIdx.y;
-  const int q0 = blockIdx.x * 2 * kTile;                 // first query row (within the batch) of this CTA
-  const int ntiles = (p.Nq - q0 > kTile) ? 2 : 1;        // second query tile present?
+  int b, h, q0, ntiles;
+  if (!fmha_work(p, b, h, q0, ntiles)) return;           // odd tile count: the second half of the last pair is empty
   const int nkv = (p.Nkv + kTile - 1) / kTile;
   const int ncomp = nkv * ntiles;
 
@@ -391,10 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.z;
-  const int h = blockIdx.y;
-  const int q0 = blockIdx.x * 2 * kTile;                 // first query row (within the batch) of this CTA
-  const int ntiles = (p.Nq - q0 > kTile) ? 2 : 1;        // second query tile present?
+  int b, h, q0, ntiles;
+  if (!fmha_work(p, b, h, q0, ntiles)) return;           // odd tile count: the second half of the last pair is empty
   const int nkv = (p.Nkv + kTile - 1) / kTile;
   const int ncomp = nkv * ntiles;
 
@@ -692,7 +710,15 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   p.scale_log2 = scale * 1.4426950408889634f;
   static const int dbg = [] { const char* e = getenv("UDT_FMHA_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
-  dim3 grid((Nq + 2 * kTile - 1) / (2 * kTile), heads, B);
+  p.pairs_per_bh = (Nq + 2 * kTile - 1) / (2 * kTile);
+  const long npairs = static_cast<long>(p.pairs_per_bh) * heads * B;
+  if (npairs > (1l << 30)) return fail(UDT_ERR_SHAPE, "udt_fmha_fwd: too many query tiles");
+  // tail wave: if its R pairs occupy at most half of the SMs, run them as 2R single-tile CTAs (UDT_FMHA_TAIL=0: never)
+  static const int tail_split = [] { const char* e = getenv("UDT_FMHA_TAIL"); return e ? atoi(e) : 1; }();
+  const int nsm = num_sms();
+  const int tail = static_cast<int>(npairs % nsm);
+  p.pairs_full = static_cast<int32_t>((tail_split && tail > 0 && 2 * tail <= nsm) ? npairs - tail : npairs);
+  dim3 grid(static_cast<unsigned>(p.pairs_full + 2 * (npairs - p.pairs_full)), 1, 1);
   // P kept in TMEM (TS-form PV MMA) is the production schedule; UDT_FMHA_TS=0 selects the smem-P kernel for A/B measurements
   static const int use_ts = [] { const char* e = getenv("UDT_FMHA_TS"); return e ? atoi(e) : 1; }();
   if (use_ts) {
