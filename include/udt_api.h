@@ -32,7 +32,7 @@ extern "C" {
 #define UDT_ACT_GEGLU 2 /* out[:, j] = x_j * gelu_erf(gate_j); weight rows interleaved per column tile */
 #define UDT_ACT_RELU 3
 
-int udt_version(void);            /* ABI version (3) */
+int udt_version(void);            /* ABI version (4: + udt_attn_local_score, udt_request_pack_u8, udt_images_to_u8) */
 int udt_arch(void);               /* compute capability of the current device *10 (100 on B200); <0 on error */
 const char* udt_last_error(void); /* thread-local message of the last failing call */
 int udt_num_sms(void);
@@ -122,6 +122,27 @@ int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o, int32_t B
  * [B*heads, N, L] (the reference's attn_map_cache, attention.py:147-174). kc/vc: fp16 [B, L, ldkv]. */
 int udt_xattn_small_l(const void* q, const void* kc, const void* vc, void* o, float* probs, int32_t B, int32_t N,
                       int32_t L, int32_t heads, int32_t ldq, int32_t ldkv, int32_t ldo, float scale, void* stream);
+
+/* Request front-end — the batch construction of demo.py:52-62,78-80 and the image export of
+ * demo.py:100-101 / test.py:94 on the device, so PCIe carries uint8:
+ * udt_request_pack_u8: image_hwc uint8 [Bs, H, W, 3], mask_hwc uint8 [Bs, H, W, MC] (0 = keep; MC <= 4) ->
+ *   image fp32 [B, 3, H, W] = u8 / 127.5 - 1, m = mean_c(mask == 0), masked = image * m, mask fp32 [B, 1, H, W] = 1 - m;
+ *   sample b reads source b % Bs (Bs = 1: one request tiled num_samples times).  Bit-exact vs the torch expressions.
+ * udt_images_to_u8: x fp32 [NB, C, HW] (NCHW, in [0, 1]) -> y uint8 [NB, HW, C] = trunc(x * 255). */
+int udt_request_pack_u8(const uint8_t* image_hwc, const uint8_t* mask_hwc, float* image, float* mask, float* masked,
+                        int32_t B, int32_t Bs, int32_t H, int32_t W, int32_t MC, void* stream);
+int udt_images_to_u8(const float* x, uint8_t* y, int32_t NB, int32_t C, int32_t HW, void* stream);
+
+/* K12 — noise-search score of one t_attn layer (loss.py:192-235 FullLoss.get_min_local_loss, read by
+ * sampling.py:340 get_init_noise):
+ *   score[b] += -min_{l < seg_l} ( max_n mask_s[b % Bm, n] * blur(mean_h probs[b*heads + h, n, l]) + 1 - seg[b % Bm, l] )
+ * probs fp32 [B*heads, N = size*size, L] (the exported attn_map), mask fp32 [Bm, H, W] sampled like
+ * F.interpolate(mask, (size, size)) (nearest), seg fp32 [Bm, seg_l], gk fp32 [ks*ks] Gaussian (zero padding ks/2,
+ * ks odd <= 7), score fp32 [B] accumulated over successive launches (zero it first; divide by the layer count).
+ * B = UNet batch ([uc; c] when CFG-doubled: B = 2*Bm). */
+int udt_attn_local_score(const float* probs, const float* mask, const float* seg, const float* gk, float* score,
+                         int32_t B, int32_t Bm, int32_t heads, int32_t size, int32_t L, int32_t seg_l, int32_t H, int32_t W,
+                         int32_t ks, void* stream);
 
 /* LabelEncoder (encoders/modules.py:1088-1173): character embedding + sinusoid positional encoding,
  * out fp16 [rows = B*L, D] = emb[idx[row], :] + pe[row % L, :] (emb fp32 [95, D], pe fp32 [L, D], idx int32), and

@@ -10,7 +10,7 @@ inference (`embedder.train = disabled_train` is installed before `model.eval()`,
 util.py:18-20), so dropout(p=0.1) makes the text embedding random.  Golden vectors are generated with the
 LabelEncoder switched to eval mode (`nn.Module.train(le, False)`) — the deterministic function both sides share.
 
-usage: python oracle/make_golden.py [tiny] [full_unet] [c1]
+usage: python oracle/make_golden.py [tiny] [loss] [full_unet] [c1]
 """
 import os
 import sys
@@ -125,11 +125,41 @@ def gen_c1(m=None, sd=None):
                 "cpu_seconds": dt, "threads": torch.get_num_threads()}, os.path.join(GOLD, "c1.pt"))
 
 
+def gen_loss():
+    """the reference's FullLoss.get_min_local_loss (loss.py:192-235) on synthetic attention maps: the one-image CFG-doubled
+    case the reference supports (sampling.py:340, [uc; c] maps against a [1, ...] mask), with the test.yaml Gaussian."""
+    m, _ = reference_engine("tiny")
+    lf = m.loss_fn
+    g = torch.Generator().manual_seed(23)
+    cache = []
+    for name, heads, size in (("output_blocks.1.1.transformer_blocks.0.t_attn", 3, 16), ("mid.attn1", 2, 16),
+                              ("input_blocks.1.1.transformer_blocks.0.t_attn", 2, 32),
+                              ("input_blocks.7.1.transformer_blocks.0.t_attn", 4, 8)):
+        probs = (torch.randn((2 * heads, size * size, 12), generator=g) * 2.0).softmax(-1)
+        cache.append({"name": name, "heads": heads, "size": size, "attn_map": probs})
+    mask = torch.zeros((1, 1, 128, 128))
+    mask[:, :, 40:72, 20:100] = 1.0
+    seg = torch.zeros((1, 12))
+    seg[0, :5] = 1.0
+    with torch.no_grad():
+        ref = lf.get_min_local_loss(cache, mask, seg)
+    k, sig = lf.gaussian_kernel_size, 1.0   # configs/test/textdesign_sd_2.yaml:113-114
+    assert torch.allclose(R.gaussian_kernel(k, sig), lf.g_kernel[0, 0], atol=1e-7)
+    mine = R.min_local_loss(cache, mask, seg, k, sig, lf.min_attn_size)
+    print("loss: reference", ref.tolist(), "restated", mine.tolist(), "min_attn_size", lf.min_attn_size)
+    assert ref.shape == (2,) and torch.allclose(mine, ref, atol=1e-7)
+    torch.save({"cache": cache, "mask": mask, "seg_mask": seg, "kernel_size": k, "sigma": sig,
+                "min_attn_size": lf.min_attn_size, "g_kernel": lf.g_kernel.clone(), "loss": ref},
+               os.path.join(GOLD, "loss.pt"))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["tiny"]
     os.makedirs(GOLD, exist_ok=True)
     if "tiny" in what:
         gen_tiny()
+    if "loss" in what:
+        gen_loss()
     m = sd = None
     if "full_unet" in what:
         m, sd = gen_full_unet()

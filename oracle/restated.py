@@ -272,6 +272,43 @@ def vae_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
 CHARSET = string.printable[:-6]  # encoders/modules.py:1097
 
 
+def gaussian_kernel(kernel_size: int = 3, sigma: float = 0.5) -> torch.Tensor:
+    """normalised 2-D Gaussian [k, k] (loss.py:103-129 get_gaussian_kernel; the reference tiles it per token channel)"""
+    ax = torch.arange(kernel_size, dtype=torch.float32)
+    yy, xx = torch.meshgrid(ax, ax, indexing="ij")
+    mean = (kernel_size - 1) / 2.0
+    g = torch.exp(-((xx - mean) ** 2 + (yy - mean) ** 2) / (2.0 * sigma ** 2)) / (2.0 * math.pi * sigma ** 2)
+    return g / g.sum()
+
+
+def min_local_loss(attn_maps: Sequence[dict], mask: torch.Tensor, seg_mask: torch.Tensor, kernel_size: int = 3,
+                   sigma: float = 0.5, min_attn_size: int = 16) -> torch.Tensor:
+    """loss.py:192-235 get_min_local_loss over items {name, heads, size, attn_map [B*heads, n, l]}: per qualifying layer
+    -min over the seg_l tokens of (max over pixels of nearest-resized mask * Gaussian-blurred head-mean map + 1 - seg_mask),
+    averaged over the layers.  The reference broadcasts a one-image mask over the CFG-doubled maps (sampling.py:307 scores
+    one image only); for B images the [uc; c] halves are scored against the same per-image masks (mask / seg repeated)."""
+    total, count = 0, 0
+    for item in attn_maps:
+        if not item["name"].endswith("t_attn") or item["size"] < min_attn_size:
+            continue
+        heads, size, am = item["heads"], item["size"], item["attn_map"].float()
+        seg_l = seg_mask.shape[1]
+        _, n, l = am.shape
+        assert seg_l <= l
+        am = am.reshape(-1, heads, n, l)[..., :seg_l].permute(0, 1, 3, 2).mean(dim=1).reshape(-1, seg_l, size, size)
+        gk = gaussian_kernel(kernel_size, sigma).to(am.device).view(1, 1, kernel_size, kernel_size).repeat(seg_l, 1, 1, 1)
+        am = F.conv2d(am, gk, padding=kernel_size // 2, groups=seg_l).reshape(-1, seg_l, n)
+        mm = F.interpolate(mask.float().to(am.device), (size, size)).tile((1, seg_l, 1, 1)).reshape(-1, seg_l, n)
+        sm = seg_mask.float().to(am.device)
+        rep = am.shape[0] // mm.shape[0]
+        if rep > 1:
+            mm, sm = mm.repeat(rep, 1, 1), sm.repeat(rep, 1)
+        p = (mm * am).max(dim=-1)[0] + (1 - sm)
+        total = total + (-p.min(dim=-1)[0])
+        count += 1
+    return total / count
+
+
 def label_indices(labels: Sequence[str], max_len: int = 12) -> torch.Tensor:
     """char -> 1..94, unknown / pad -> 0 (encoders/modules.py:1149-1158)"""
     rows = []
@@ -348,6 +385,35 @@ def euler_sample(unet_sd: SD, noise: torch.Tensor, c: dict, uc: dict, n_steps: i
             trace.append(eps.clone())
         x = x + (sig[i + 1] - sig[i]) * eps
     return x
+
+
+def init_noise_search(unet_sd: SD, noises: Sequence[torch.Tensor], c: dict, uc: dict, mask: torch.Tensor, seg_mask: torch.Tensor,
+                      scale: float, kernel_size: int = 3, sigma: float = 1.0, min_attn_size: int = 16
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """sampling.py:264-322 get_init_noise: every trial noise is sampled for 2 steps (prepare_sampling_loop num_steps=2),
+    scored by get_min_local_loss on the attention maps of the LAST step (conditional half, sampling.py:340-341) and the
+    lowest score wins (first one on ties: stable sort).  The reference scores one image (`.item()`); here every image keeps
+    its own winner.  Returns (best noise [B,4,h,w], losses [iters, B]).  The reference function itself hard-codes a cuda
+    device (sampling.py:269,311) and cannot run in the build container: this composition is unpinned as a whole, its parts
+    (cfg_denoise_eps + exported maps: tests/golden/tiny.pt; min_local_loss: tests/golden/loss.pt) are pinned."""
+    sig = sampler_sigmas(2)
+    table = denoiser_sigmas()
+    losses = []
+    for noise in noises:
+        x = noise * torch.sqrt(1.0 + sig[0] ** 2.0)
+        for i in range(2):
+            probs: List[torch.Tensor] = []
+            eps = cfg_denoise_eps(unet_sd, x, float(sig[i]), table, c, uc, scale, probs_out=probs)
+            x = x + (sig[i + 1] - sig[i]) * eps
+        b2 = 2 * noise.shape[0]
+        items = [{"name": f"{k}.t_attn", "heads": p.shape[0] // b2, "size": int(round(p.shape[1] ** 0.5)), "attn_map": p}
+                 for k, p in enumerate(probs)]
+        loss = min_local_loss(items, mask, seg_mask, kernel_size, sigma, min_attn_size)
+        losses.append(loss[loss.shape[0] // 2:])
+    losses_t = torch.stack(losses)                              # [iters, B]
+    pick = losses_t.argmin(dim=0)                               # first minimum
+    best = torch.stack([noises[int(pick[j])][j] for j in range(noises[0].shape[0])])
+    return best, losses_t
 
 
 def predict(sd: SD, batch: dict, n_steps: int, scale: float, scale_factor: float = 0.18215) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -151,25 +151,39 @@ def test_shard_bounds_cover_the_batch():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
 
 
-def test_min_local_loss_matches_formula():
-    """FullLoss.get_min_local_loss against a direct evaluation of loss.py:192-235's formula, incl. batch > 1"""
+def test_full_loss_host_object_has_no_cpu_path():
+    """FullLoss keeps the reference's Gaussian buffer (loss.py:103-129) and scores on the CUDA kernel only"""
+    from oracle import restated as R
     from udifftext_b200.host.loss import FullLoss
     g = torch.Generator().manual_seed(5)
     loss = FullLoss(seq_len=12, kernel_size=3, gaussian_sigma=1.0, min_attn_size=4)
     assert abs(loss.g_kernel.sum().item() - 12.0) < 1e-5 and tuple(loss.g_kernel.shape) == (12, 1, 3, 3)
-    b, heads, size = 2, 2, 4
-    probs = torch.rand((2 * b * heads, size * size, 12), generator=g).softmax(-1)
-    cache = [{"name": "blk.t_attn", "heads": heads, "size": size, "attn_map": probs},
-             {"name": "blk.small.t_attn", "heads": heads, "size": 2, "attn_map": torch.rand((2 * b * heads, 4, 12), generator=g)}]
+    assert torch.allclose(loss.g_kernel[3, 0], R.gaussian_kernel(3, 1.0), atol=1e-7)
+    cache = [{"name": "blk.t_attn", "heads": 2, "size": 4, "attn_map": torch.rand((4, 16, 12), generator=g).softmax(-1)}]
+    with pytest.raises(RuntimeError):
+        loss.get_min_local_loss(cache, torch.ones((1, 1, 32, 32)), torch.ones((1, 12)))
+
+
+def test_oracle_min_local_loss_batch_generalisation():
+    """the oracle's B-image form of loss.py:192-235 equals the reference's one-image form evaluated image by image"""
+    from oracle import restated as R
+    g = torch.Generator().manual_seed(6)
+    b, heads, size = 3, 2, 8
+    probs = torch.rand((2 * b, heads, size * size, 12), generator=g).softmax(-1)          # [uc images; c images]
+    cache = [{"name": "blk.t_attn", "heads": heads, "size": size, "attn_map": probs.reshape(-1, size * size, 12)},
+             {"name": "blk.attn1", "heads": heads, "size": size, "attn_map": probs.reshape(-1, size * size, 12)},
+             {"name": "small.t_attn", "heads": heads, "size": 2, "attn_map": torch.rand((2 * b * heads, 4, 12), generator=g)}]
     mask = (torch.rand((b, 1, 32, 32), generator=g) > 0.5).float()
-    seg = torch.zeros((b, 12)); seg[0, :3] = 1; seg[1, :7] = 1
-    got = loss.get_min_local_loss(cache, mask, seg)
+    seg = torch.zeros((b, 12))
+    for i, n in enumerate((3, 7, 12)):
+        seg[i, :n] = 1
+    got = R.min_local_loss(cache, mask, seg, 3, 1.0, 4)
     assert got.shape == (2 * b,)
-    am = probs.reshape(2 * b, heads, size * size, 12).mean(1).permute(0, 2, 1).reshape(2 * b, 12, size, size)
-    am = F.conv2d(am, loss.g_kernel, padding=1, groups=12).reshape(2 * b, 12, -1)
-    mm = F.interpolate(mask, (size, size)).reshape(b, 1, -1).repeat(2, 12, 1)
-    expect = -((mm * am).max(-1)[0] + (1 - seg.repeat(2, 1))).min(-1)[0]
-    assert torch.allclose(got, expect, atol=1e-6)
+    for i in range(b):
+        one = [{"name": "blk.t_attn", "heads": heads, "size": size,
+                "attn_map": probs[[i, b + i]].reshape(-1, size * size, 12)}]
+        ref = R.min_local_loss(one, mask[i:i + 1], seg[i:i + 1], 3, 1.0, 4)
+        assert torch.allclose(got[[i, b + i]], ref, atol=1e-7)
 
 
 def test_dropin_sgm_package_resolves_reference_paths():

@@ -536,3 +536,72 @@ def test_folded_cross_attention_matches_direct(udt_lib, b, n, heads, l):
     torch.cuda.synchronize()
     assert _rel(t.cpu(), ref) < 3e-3
     assert (probs.cpu() - pr.reshape(b * heads, n, l)).abs().max().item() < 5e-3
+
+
+# ------------------------------------------------------------------------------------------- K12 noise-search score
+def test_attn_local_score_matches_reference_golden(udt_lib):
+    """FullLoss.get_min_local_loss on the CUDA kernel vs the reference's own output (tests/golden/loss.pt)"""
+    import os
+    from udifftext_b200.host.loss import FullLoss
+    dev = _dev()
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "loss.pt"))
+    loss = FullLoss(seq_len=12, kernel_size=gold["kernel_size"], gaussian_sigma=gold["sigma"],
+                    min_attn_size=gold["min_attn_size"]).to(dev)
+    cache = [dict(it, attn_map=it["attn_map"].to(dev)) for it in gold["cache"]]
+    got = loss.get_min_local_loss(cache, gold["mask"].to(dev), gold["seg_mask"].to(dev))
+    torch.cuda.synchronize()
+    assert torch.allclose(got.cpu(), gold["loss"], atol=2e-6), (got.cpu(), gold["loss"])
+
+
+@pytest.mark.parametrize("b,heads,size,hw,ks", [(1, 5, 64, 512, 3), (4, 10, 32, 512, 3), (3, 20, 16, 200, 5), (2, 5, 96, 768, 3)])
+def test_attn_local_score_matches_oracle(udt_lib, b, heads, size, hw, ks):
+    """batch > 1 (per-image masks and string lengths), non-integer mask scale, 5x5 Gaussian, 96x96 maps (C5)"""
+    from oracle import restated as R
+    from udifftext_b200.host.loss import FullLoss
+    dev = _dev()
+    g = torch.Generator().manual_seed(b * size + heads)
+    probs = (_randn((2 * b * heads, size * size, 12), g) * 2.0).softmax(-1)
+    cache = [{"name": "a.t_attn", "heads": heads, "size": size, "attn_map": probs},
+             {"name": "b.t_attn", "heads": heads, "size": size, "attn_map": probs.flip(0).contiguous()}]
+    mask = (torch.rand((b, 1, hw, hw), generator=g) > 0.7).float()
+    seg = torch.zeros((b, 12))
+    for i in range(b):
+        seg[i, : 1 + (5 * i + 3) % 12] = 1
+    ref = R.min_local_loss(cache, mask, seg, ks, 1.0, 16)
+    loss = FullLoss(seq_len=12, kernel_size=ks, gaussian_sigma=1.0, min_attn_size=16).to(dev)
+    got = loss.get_min_local_loss([dict(it, attn_map=it["attn_map"].to(dev)) for it in cache], mask.to(dev), seg.to(dev))
+    torch.cuda.synchronize()
+    assert got.shape == (2 * b,)
+    assert torch.allclose(got.cpu(), ref, atol=2e-6), (got.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------- request front-end (uint8 I/O)
+@pytest.mark.parametrize("hh,ww,mc,ns", [(512, 512, 3, 4), (64, 96, 1, 3), (37, 53, 4, 1)])
+def test_request_pack_u8_is_bit_exact(udt_lib, hh, ww, mc, ns):
+    """demo.py:52-62,78-80 (image / 127.5 - 1, mask == 0 mean over channels, masked, 1 - mask, tile) — bit-exact"""
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(hh + ww)
+    img = torch.randint(0, 256, (hh, ww, 3), generator=g, dtype=torch.uint8)
+    msk = (torch.randint(0, 3, (hh, ww, mc), generator=g) * 127).to(torch.uint8)
+    image = img.permute(2, 0, 1).to(torch.float32) / 127.5 - 1.0
+    m = (msk == 0).to(torch.int32).permute(2, 0, 1).to(torch.float32).mean(dim=0, keepdim=True)
+    masked, mask = image * m, 1 - m
+    got = ops.request_pack_u8(img[None].to(dev), msk[None].to(dev), ns)
+    torch.cuda.synchronize()
+    for t, ref in zip(got, (image, mask, masked)):
+        assert torch.equal(t.cpu(), torch.tile(ref[None], (ns, 1, 1, 1)))
+
+
+def test_images_to_u8_is_bit_exact(udt_lib):
+    """demo.py:100-101: (samples.cpu().numpy().transpose(0, 2, 3, 1) * 255).astype(uint8)"""
+    import numpy as np
+    from udifftext_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand((3, 3, 40, 56), generator=g)
+    x[0, 0, 0, :8] = torch.tensor([0.0, 1.0, 0.5, 1 / 255, 254.999 / 255, 0.999999, 2 / 255, 128 / 255])
+    ref = (x.numpy().transpose(0, 2, 3, 1) * 255).astype(np.uint8)
+    got = ops.images_to_u8(x.to(dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), ref)

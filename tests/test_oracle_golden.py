@@ -76,3 +76,13 @@ def test_oracle_full_unet_matches_reference_golden():
     with torch.no_grad():
         out = R.unet_forward(sd, gold["x"], gold["t"], gold["ctx"])
     assert _rel(out, gold["out"]) < 1e-5
+
+
+def test_oracle_min_local_loss_matches_reference_golden():
+    """noise-search score (loss.py:192-235) against the reference's own FullLoss.get_min_local_loss output"""
+    from oracle import restated as R
+    gold = torch.load(os.path.join(GOLD, "loss.pt"))
+    assert torch.allclose(R.gaussian_kernel(gold["kernel_size"], gold["sigma"]), gold["g_kernel"][0, 0], atol=1e-7)
+    got = R.min_local_loss(gold["cache"], gold["mask"], gold["seg_mask"], gold["kernel_size"], gold["sigma"], gold["min_attn_size"])
+    assert torch.allclose(got, gold["loss"], atol=1e-7)
+    assert gold["loss"].abs().min() > 1e-3   # not vacuous: the masked region carries attention

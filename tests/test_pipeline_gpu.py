@@ -106,3 +106,77 @@ def test_c1_full_predict_matches_reference(udt_lib):
     ez, ep = _rel(z, gold["z"]), _rel(img, gold["pixels_f16"])
     print(f"C1 predict: z rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}, max-abs {(img.cpu() - gold['pixels_f16'].float()).abs().max():.3e}")
     assert ez < 3e-2 and ep < 3e-2
+
+
+def test_request_batch_u8_matches_fp32_request(tiny_engine):
+    """demo.py:52-101 through the uint8 front-end: same batch tensors, same images as the fp32 host-built request"""
+    from udifftext_b200 import api
+    model = tiny_engine
+    cfgs = api.runtime_config(steps=3, batch_size=2, H=64, W=64, seq_len=12)
+    sampler = api.init_sampling(cfgs)
+    sampler.verbose = False
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (64, 64, 3), generator=g, dtype=torch.uint8)
+    msk = torch.zeros((64, 64, 3), dtype=torch.uint8)
+    msk[16:32, 8:56] = 255
+    # the reference's host-side construction (demo.py:57-98)
+    image = img.permute(2, 0, 1).to(torch.float32) / 127.5 - 1.0
+    m = (msk == 0).to(torch.int32).permute(2, 0, 1).to(torch.float32).mean(dim=0, keepdim=True)
+    text = "Hello"
+    tile4 = lambda t: torch.tile(t[None], (2, 1, 1, 1))
+    tile2 = lambda t: torch.tile(t[None], (2, 1))
+    ref_batch = {"image": tile4(image), "mask": tile4(1 - m), "masked": tile4(image * m),
+                 "seg_mask": tile2(torch.cat((torch.ones(5), torch.zeros(7)))), "label": [text] * 2, "txt": [f'"{text}"'] * 2,
+                 "original_size_as_tuple": tile2(torch.tensor((64, 64))), "crop_coords_top_left": tile2(torch.tensor((0, 0))),
+                 "target_size_as_tuple": tile2(torch.tensor((64, 64))), "name": ["0"] * 2}
+    batch = api.request_batch_u8(cfgs, img.numpy(), msk.numpy(), text, 2)
+    for k in ("image", "mask", "masked"):
+        assert torch.equal(batch[k].cpu(), ref_batch[k]), k
+    assert torch.equal(batch["seg_mask"], ref_batch["seg_mask"]) and batch["txt"] == ref_batch["txt"]
+    torch.manual_seed(21)
+    a, _ = api.predict(cfgs, model, sampler, batch)
+    torch.manual_seed(21)
+    b, _ = api.predict(cfgs, model, sampler, ref_batch)
+    assert torch.equal(a, b)
+    u8 = api.images_to_u8(a)
+    assert u8.dtype == torch.uint8 and tuple(u8.shape) == (2, 64, 64, 3)
+    assert torch.equal(u8.cpu(), (a.cpu().permute(0, 2, 3, 1) * 255).to(torch.uint8))
+
+
+@pytest.mark.parametrize("b", [1, 3])
+def test_noise_search_matches_oracle(tiny_engine, b):
+    """get_init_noise with noise_iters > 0 (sampling.py:264-322; the reference's default inference mode): the trial
+    scores (attention-map export + K12) follow the oracle and every image keeps the same winning noise; batch 3 is the
+    generalisation the reference cannot run (`.item()`)."""
+    from oracle import restated as R
+    from udifftext_b200 import api, synth
+    dev = torch.device("cuda", 0)
+    sd = synth.synthetic_state_dict(synth.load_manifest("tiny"), 1234)
+    iters = 4
+    cfgs = api.runtime_config(steps=3, batch_size=b, noise_iters=iters)
+    sampler = api.init_sampling(cfgs)
+    batch = synth.synthetic_batch(40 + b, b, 64, 64, None)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        dbatch, dbatch_uc = api.prepare_batch(cfgs, dict(batch))
+        c, uc = tiny_engine.conditioner.get_unconditional_conditioning(dbatch, batch_uc=dbatch_uc,
+                                                                      force_uc_zero_embeddings=["label"])
+        torch.manual_seed(78)
+        best = sampler.get_init_noise(cfgs, tiny_engine, cond=c, batch=dbatch, uc=uc)
+    torch.cuda.synchronize()
+    torch.manual_seed(78)
+    noises = [torch.randn((b, 4, 8, 8)).to(dev) for _ in range(iters + 1)][:iters]   # one unused draw after the last trial
+    with torch.no_grad():
+        ref_best, ref_losses = R.init_noise_search(
+            {k: v.to(dev) for k, v in R._sub(sd, "model.diffusion_model.").items()}, noises,
+            {k: v.float() for k, v in c.items()}, {k: v.float() for k, v in uc.items()}, dbatch["mask"], dbatch["seg_mask"],
+            5.0, 3, 1.0, 4)
+    got = sampler.last_init_losses
+    assert got.shape == (iters, b)
+    err = (got - ref_losses).abs().max().item()
+    print(f"noise search b={b}: losses {got.flatten().tolist()} vs oracle {ref_losses.flatten().tolist()} (max abs err {err:.2e})")
+    assert err < 1e-2 * ref_losses.abs().max().item() + 2e-4
+    gaps = ref_losses.sort(dim=0)[0]
+    for j in range(b):
+        if (gaps[1, j] - gaps[0, j]).item() > 4 * err:        # a clear winner: the same noise must be kept
+            assert torch.equal(best[j], ref_best[j])

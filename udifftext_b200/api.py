@@ -11,7 +11,7 @@ from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
-from . import synth
+from . import ops, synth
 from .host import rng
 from .host.config import AttrDict, instantiate_from_config, load_yaml, to_attr
 from .host.sampler import EulerEDMSampler
@@ -119,6 +119,41 @@ def prepare_batch(cfgs, batch: Dict) -> Tuple[Dict, Dict]:
     if "label" in batch:
         batch_uc["label"] = ["" for _ in batch["label"]]
     return batch, batch_uc
+
+
+# ------------------------------------------------------------------------------------------------- demo.py:52-101
+def request_batch_u8(cfgs, image_u8, mask_u8, text: str, num_samples: int, name: str = "0") -> Dict:
+    """demo.py:52-98 with the pixel work on the device: `image_u8` uint8 [H, W, 3] and `mask_u8` uint8 [H, W, 3] (the
+    user's brush mask, 0 = keep) already resized to cfgs.H x cfgs.W (cv2.resize stays with the caller) are copied as
+    uint8 (1 MB instead of 7.3 MB of fp32 per sample) and expanded by `udt_request_pack_u8`; the returned batch dict
+    has the reference's schema with device tensors and goes straight into `predict`."""
+    dev = torch.device("cuda", index=cfgs.gpu)
+    img = torch.as_tensor(image_u8)
+    msk = torch.as_tensor(mask_u8)
+    if msk.dim() == 2:
+        msk = msk[..., None]
+    if img.dtype != torch.uint8 or msk.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3 or msk.shape[:2] != img.shape[:2]:
+        raise ValueError("request_batch_u8: image uint8 [H, W, 3] and mask uint8 [H, W(, C)] of the same size expected")
+    seq_len = int(getattr(cfgs, "seq_len", 12))          # configs/demo.yaml:10
+    if len(text) > seq_len:
+        raise ValueError(f"text longer than seq_len={seq_len}")
+    hh, ww = int(img.shape[0]), int(img.shape[1])
+    image, mask, masked = ops.request_pack_u8(img.contiguous()[None].to(dev, non_blocking=True),
+                                              msk.contiguous()[None].to(dev, non_blocking=True), num_samples)
+    seg = torch.cat((torch.ones(len(text)), torch.zeros(seq_len - len(text))))
+    tile = lambda t: torch.tile(t[None], (num_samples, 1))
+    return {
+        "image": image, "mask": mask, "masked": masked, "seg_mask": tile(seg),
+        "label": [text] * num_samples, "txt": [f'"{text}"'] * num_samples,
+        "original_size_as_tuple": tile(torch.tensor((hh, ww))), "crop_coords_top_left": tile(torch.tensor((0, 0))),
+        "target_size_as_tuple": tile(torch.tensor((hh, ww))), "name": [name] * num_samples,
+    }
+
+
+def images_to_u8(samples: torch.Tensor) -> torch.Tensor:
+    """demo.py:100-101 / test.py:94: decoded images [B, 3, H, W] in [0, 1] -> uint8 [B, H, W, 3] on the device
+    (`(x * 255).astype(uint8)`); the caller's `.cpu()` then moves a quarter of the bytes"""
+    return ops.images_to_u8(samples.contiguous())
 
 
 # ------------------------------------------------------------------------------------------------- test.py:19-40

@@ -553,6 +553,118 @@ inline int grid_for(size_t total, int threads) {
   return static_cast<int>(g < cap ? (g == 0 ? 1 : g) : cap);
 }
 
+// ---------------------------------------------------------------------------------------------- request front-end
+// demo.py:52-62 on the device: uint8 HWC request image + uint8 HWC user mask (0 = keep, anything else = synthesise) ->
+// image fp32 NCHW in [-1, 1], m = mean_c(mask == 0), masked = image * m, mask = 1 - m; source s = b % Bs is tiled over the
+// batch (demo.py:78-80).  Same fp32 operations in the same order as the reference's torch expressions: bit-exact.
+__global__ void request_pack_u8_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ msk, float* __restrict__ image,
+                                       float* __restrict__ mask, float* __restrict__ masked, int B, int Bs, int HW, int MC) {
+  griddep_launch();
+  griddep_wait();
+  const size_t total = static_cast<size_t>(B) * HW;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i % HW);
+    const int b = static_cast<int>(i / HW);
+    const size_t sp = static_cast<size_t>(b % Bs) * HW + p;
+    float m = 0.0f;
+    for (int c = 0; c < MC; ++c) m += (msk[sp * MC + c] == 0) ? 1.0f : 0.0f;
+    m = __fdiv_rn(m, static_cast<float>(MC));
+    mask[i] = 1.0f - m;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fsub_rn(__fdiv_rn(static_cast<float>(img[sp * 3 + c]), 127.5f), 1.0f);
+      const size_t o = (static_cast<size_t>(b) * 3 + c) * HW + p;
+      image[o] = v;
+      masked[o] = __fmul_rn(v, m);
+    }
+  }
+}
+
+// demo.py:100-101 / test.py:94: fp32 NCHW in [0, 1] -> uint8 NHWC, (x * 255) truncated like numpy's astype(uint8)
+__global__ void images_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int NB, int C, int HW) {
+  griddep_launch();
+  griddep_wait();
+  const size_t total = static_cast<size_t>(NB) * HW * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t r = i / C;
+    const int p = static_cast<int>(r % HW);
+    const int n = static_cast<int>(r / HW);
+    const float v = __fmul_rn(x[(static_cast<size_t>(n) * C + c) * HW + p], 255.0f);
+    y[i] = static_cast<uint8_t>(static_cast<int>(fminf(fmaxf(v, 0.0f), 255.0f)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K12
+// Noise-search score of one t_attn layer (loss.py:192-235 get_min_local_loss): one CTA per UNet sample b.  For every
+// valid token l the head-mean attention map is gathered into shared memory, blurred with the ks x ks Gaussian (zero
+// padding, cross-correlation like F.conv2d), multiplied by the nearest-sampled inpainting mask and max-reduced over the
+// pixels; score[b] += -min_l (max + 1 - seg[l]).  max / min are order independent and the head sum runs in a fixed
+// order, so the result is deterministic; the layers are accumulated in launch order on the stream.
+constexpr int kLsThreads = 512;
+constexpr int kLsMaxK = 7;
+
+__global__ void __launch_bounds__(kLsThreads) attn_local_score_kernel(const float* __restrict__ probs,
+                                                                      const float* __restrict__ mask,
+                                                                      const float* __restrict__ seg,
+                                                                      const float* __restrict__ gk, float* __restrict__ score,
+                                                                      int Bm, int heads, int size, int L, int seg_l, int H, int W,
+                                                                      int ks) {
+  griddep_launch();
+  griddep_wait();
+  extern __shared__ float ls_sm[];
+  __shared__ float red[kLsThreads / 32];
+  __shared__ float s_gk[kLsMaxK * kLsMaxK];
+  const int N = size * size;
+  float* hm = ls_sm;        // [N] head-mean attention of the current token
+  float* mk = ls_sm + N;    // [N] mask sampled at the map resolution
+  const int b = blockIdx.x;
+  const int bm = b % Bm;    // CFG-doubled UNet batch [uc; c]: both halves score against the same per-image mask
+  const int pad = ks / 2;
+  const float sy = static_cast<float>(H) / static_cast<float>(size), sx = static_cast<float>(W) / static_cast<float>(size);
+  if (threadIdx.x < ks * ks) s_gk[threadIdx.x] = gk[threadIdx.x];
+  for (int n = threadIdx.x; n < N; n += kLsThreads) {
+    const int y = n / size, x = n - y * size;
+    const int yy = min(static_cast<int>(floorf(y * sy)), H - 1), xx = min(static_cast<int>(floorf(x * sx)), W - 1);
+    mk[n] = mask[(static_cast<size_t>(bm) * H + yy) * W + xx];
+  }
+  const float inv_heads = 1.0f / static_cast<float>(heads);
+  float best = INFINITY;
+  for (int l = 0; l < seg_l; ++l) {
+    __syncthreads();   // previous token's hm fully consumed (and mk / s_gk written, first time round)
+    for (int n = threadIdx.x; n < N; n += kLsThreads) {
+      float acc = 0.0f;
+      for (int h = 0; h < heads; ++h) acc += probs[((static_cast<size_t>(b) * heads + h) * N + n) * L + l];
+      hm[n] = acc * inv_heads;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int n = threadIdx.x; n < N; n += kLsThreads) {
+      const int y = n / size, x = n - y * size;
+      float v = 0.0f;
+      for (int i = 0; i < ks; ++i) {
+        const int yy = y + i - pad;
+        if (yy < 0 || yy >= size) continue;
+        for (int j = 0; j < ks; ++j) {
+          const int xx = x + j - pad;
+          if (xx >= 0 && xx < size) v = fmaf(s_gk[i * ks + j], hm[yy * size + xx], v);
+        }
+      }
+      mx = fmaxf(mx, mk[n] * v);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < kLsThreads / 32; ++i) mx = fmaxf(mx, red[i]);
+      best = fminf(best, mx + (1.0f - seg[bm * seg_l + l]));
+    }
+  }
+  if (threadIdx.x == 0) score[b] += -best;
+}
+
 }  // namespace
 
 using udt_host::check_launch;
@@ -719,4 +831,48 @@ extern "C" int udt_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* y, 
   udt_host::launch_pdl(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, x_is_fp32, y, NB, C, HW, ld, scale, shift, clamp01);
   return check_launch("udt_nhwc_to_nchw_f32");
+}
+
+extern "C" int udt_attn_local_score(const float* probs, const float* mask, const float* seg, const float* gk, float* score,
+                                    int32_t B, int32_t Bm, int32_t heads, int32_t size, int32_t L, int32_t seg_l, int32_t H,
+                                    int32_t W, int32_t ks, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (B < 1 || Bm < 1 || B % Bm || heads < 1 || size < 1 || L < 1 || seg_l < 1 || seg_l > L || H < 1 || W < 1 || ks < 1 ||
+      ks > kLsMaxK || (ks & 1) == 0)
+    return fail(UDT_ERR_SHAPE, "udt_attn_local_score: B=%d Bm=%d heads=%d size=%d L=%d seg_l=%d ks=%d", B, Bm, heads, size, L,
+                seg_l, ks);
+  const size_t smem = static_cast<size_t>(2) * size * size * sizeof(float);
+  if (smem > 200 * 1024) return fail(UDT_ERR_SHAPE, "udt_attn_local_score: map %dx%d does not fit shared memory", size, size);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_local_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(attn score smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  udt_host::launch_pdl(attn_local_score_kernel, dim3(B), dim3(kLsThreads), smem, reinterpret_cast<cudaStream_t>(stream), probs,
+                       mask, seg, gk, score, Bm, heads, size, L, seg_l, H, W, ks);
+  return check_launch("udt_attn_local_score");
+}
+
+extern "C" int udt_request_pack_u8(const uint8_t* image_hwc, const uint8_t* mask_hwc, float* image, float* mask, float* masked,
+                                   int32_t B, int32_t Bs, int32_t H, int32_t W, int32_t MC, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (B < 1 || Bs < 1 || B % Bs || H < 1 || W < 1 || MC < 1 || MC > 4)
+    return fail(UDT_ERR_SHAPE, "udt_request_pack_u8: B=%d Bs=%d H=%d W=%d MC=%d", B, Bs, H, W, MC);
+  const size_t total = static_cast<size_t>(B) * H * W;
+  udt_host::launch_pdl(request_pack_u8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                       image_hwc, mask_hwc, image, mask, masked, B, Bs, H * W, MC);
+  return check_launch("udt_request_pack_u8");
+}
+
+extern "C" int udt_images_to_u8(const float* x, uint8_t* y, int32_t NB, int32_t C, int32_t HW, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (NB < 1 || C < 1 || HW < 1) return fail(UDT_ERR_SHAPE, "udt_images_to_u8: NB=%d C=%d HW=%d", NB, C, HW);
+  const size_t total = static_cast<size_t>(NB) * C * HW;
+  udt_host::launch_pdl(images_to_u8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), x, y,
+                       NB, C, HW);
+  return check_launch("udt_images_to_u8");
 }

@@ -7,7 +7,6 @@ import math
 from typing import List
 
 import torch
-import torch.nn.functional as F
 
 
 class FullLoss:
@@ -37,25 +36,27 @@ class FullLoss:
 
     def get_min_local_loss(self, attn_map_cache: List[dict], mask: torch.Tensor, seg_mask: torch.Tensor) -> torch.Tensor:
         """-min over valid tokens of max over pixels of (mask * blurred head-mean attention), averaged over the
-        `t_attn` layers whose map is at least `min_attn_size` wide (loss.py:192-235).  Returns [B_unet]."""
-        total, count = 0, 0
-        for item in attn_map_cache:
-            if not item["name"].endswith("t_attn") or item["size"] is None or item["size"] < self.min_attn_size:
-                continue
-            heads, size, am = item["heads"], item["size"], item["attn_map"]
-            seg_l = seg_mask.shape[1]
-            _, n, l = am.shape
-            assert seg_l <= l
-            am = am.reshape(-1, heads, n, l)[..., :seg_l].mean(dim=1).permute(0, 2, 1)            # b, l, n
-            am = F.conv2d(am.reshape(-1, seg_l, size, size), self.g_kernel.to(am.device),
-                          padding=self.gaussian_kernel_size // 2, groups=seg_l).reshape(-1, seg_l, n)
-            mm = F.interpolate(mask.to(am.device), (size, size)).tile((1, seg_l, 1, 1)).reshape(-1, seg_l, n)
-            sm = seg_mask.to(am.device)
-            if am.shape[0] == 2 * mm.shape[0] and mm.shape[0] > 1:
-                # CFG-doubled UNet batch [uc; c]: the reference relies on broadcasting and therefore only works for
-                # one image (sampling.py:307); repeating the per-image masks lifts that limit with identical values
-                mm, sm = torch.cat([mm, mm]), torch.cat([sm, sm])
-            p = (mm * am).max(dim=-1)[0] + (1 - sm)
-            total = total + (-p.min(dim=-1)[0])
-            count += 1
-        return total / count
+        `t_attn` layers whose map is at least `min_attn_size` wide (loss.py:192-235).  Returns [B_unet].  One K12
+        launch (`udt_attn_local_score`) per layer; CUDA tensors only — there is no CPU path.
+
+        The reference relies on broadcasting the [1, l, n] mask against the CFG-doubled [2, l, n] maps and therefore
+        only works for one image (`.item()`, sampling.py:307); the kernel indexes the per-image mask / seg_mask with
+        `b % B_images`, which lifts that limit with identical values."""
+        layers = [it for it in attn_map_cache
+                  if it["name"].endswith("t_attn") and it["size"] is not None and it["size"] >= self.min_attn_size]
+        if not layers:
+            raise ValueError("get_min_local_loss: no exported t_attn map of at least min_attn_size")
+        dev = layers[0]["attn_map"].device
+        if dev.type != "cuda":
+            raise RuntimeError("FullLoss.get_min_local_loss runs on the CUDA kernels only (no CPU path)")
+        from .. import ops
+        mask = mask.to(dev, torch.float32).contiguous()
+        seg = seg_mask.to(dev, torch.float32).contiguous()
+        gk = self.g_kernel[0, 0].to(dev, torch.float32).contiguous()
+        b_unet = layers[0]["attn_map"].shape[0] // layers[0]["heads"]
+        assert b_unet % mask.shape[0] == 0 and seg.shape[0] == mask.shape[0]
+        score = torch.zeros((b_unet,), device=dev, dtype=torch.float32)
+        for it in layers:
+            assert seg.shape[1] <= it["attn_map"].shape[2]
+            ops.attn_local_score(it["attn_map"].contiguous(), mask, seg, gk, score, it["heads"], it["size"])
+        return score / len(layers)

@@ -97,6 +97,7 @@ class EulerEDMSampler(EDMSampler):
         verbose, self.verbose = self.verbose, False
         best_noise, best_loss = randn.clone(), torch.full((shape[0],), float("inf"), device=dev)
         worst = torch.full((shape[0],), -float("inf"), device=dev)
+        trial_losses = []
         for _ in range(iters):
             x = randn.clone()
             x, _, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps=2)
@@ -106,12 +107,14 @@ class EulerEDMSampler(EDMSampler):
                 runner.step(i, export_attn_maps=True)
             loss = model.loss_fn.get_min_local_loss(model.model.diffusion_model.attn_map_cache, batch["mask"], batch["seg_mask"])
             loss = loss[loss.shape[0] // 2:]                      # conditional half of the CFG batch (:341)
+            trial_losses.append(loss)
             better = loss < best_loss
             best_noise[better] = randn[better]
             best_loss = torch.minimum(best_loss, loss)
             worst = torch.maximum(worst, loss)
             randn = rng.randn(shape, dev)                         # a fresh draw per iteration (:311), used or not
         self.verbose = verbose
+        self.last_init_losses = torch.stack(trial_losses)         # [noise_iters, B], for inspection / tests
         print(f"Init local loss: Best {best_loss.tolist()} Worst {worst.tolist()}")
         return best_noise
 

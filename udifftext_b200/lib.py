@@ -55,6 +55,11 @@ _PROTOTYPES = {
                                c_int32, c_int32, c_float, c_void_p]),
     "udt_xattn_small_l": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "udt_request_pack_u8": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                      c_int32, c_void_p]),
+    "udt_images_to_u8": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "udt_attn_local_score": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "udt_label_embed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "udt_mha_small": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "udt_softmax_rows": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),

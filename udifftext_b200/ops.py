@@ -338,6 +338,42 @@ def softmax_groups(x: torch.Tensor, groups: int, l: int, out: Optional[torch.Ten
     return out
 
 
+def request_pack_u8(image_u8: torch.Tensor, mask_u8: torch.Tensor, b: int):
+    """uint8 [Bs, H, W, 3] image + uint8 [Bs, H, W, MC] user mask (device) -> (image, mask, masked) fp32 NCHW, demo.py:52-62"""
+    bs, hh, ww, _ = image_u8.shape
+    assert image_u8.dtype == mask_u8.dtype == torch.uint8 and image_u8.is_contiguous() and mask_u8.is_contiguous()
+    assert image_u8.shape[3] == 3 and mask_u8.shape[:3] == image_u8.shape[:3]
+    dev = image_u8.device
+    image = torch.empty((b, 3, hh, ww), device=dev, dtype=torch.float32)
+    masked = torch.empty_like(image)
+    mask = torch.empty((b, 1, hh, ww), device=dev, dtype=torch.float32)
+    _invoke("udt_request_pack_u8", image_u8.data_ptr(), mask_u8.data_ptr(), image.data_ptr(), mask.data_ptr(), masked.data_ptr(),
+            b, bs, hh, ww, mask_u8.shape[3])
+    return image, mask, masked
+
+
+def images_to_u8(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW [B, C, H, W] in [0, 1] -> uint8 NHWC, trunc(x * 255) (demo.py:100-101)"""
+    b, c, hh, ww = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty((b, hh, ww, c), device=x.device, dtype=torch.uint8)
+    _invoke("udt_images_to_u8", x.data_ptr(), y.data_ptr(), b, c, hh * ww)
+    return y
+
+
+def attn_local_score(probs: torch.Tensor, mask: torch.Tensor, seg: torch.Tensor, gk: torch.Tensor, score: torch.Tensor,
+                     heads: int, size: int) -> None:
+    """score[b] += noise-search score of one t_attn layer (K12, loss.py:192-235): probs fp32 [B*heads, size*size, L],
+    mask fp32 [Bm, 1, H, W], seg fp32 [Bm, seg_l], gk fp32 [ks, ks], score fp32 [B] (B = Bm or 2*Bm)"""
+    b = score.shape[0]
+    bm, _, hh, ww = mask.shape
+    assert probs.is_contiguous() and mask.is_contiguous() and seg.is_contiguous() and gk.is_contiguous()
+    assert probs.dtype == mask.dtype == seg.dtype == gk.dtype == score.dtype == torch.float32
+    assert probs.shape[0] == b * heads and probs.shape[1] == size * size
+    _invoke("udt_attn_local_score", probs.data_ptr(), mask.data_ptr(), seg.data_ptr(), gk.data_ptr(), score.data_ptr(),
+            b, bm, heads, size, probs.shape[2], seg.shape[1], hh, ww, gk.shape[-1])
+
+
 def label_embed(idx: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
     """idx int32 [B, L]; emb fp32 [V, D]; pe fp32 [L, D] -> fp16 [B*L, D]"""
     b, l = idx.shape
