@@ -392,6 +392,138 @@ __global__ void __launch_bounds__(kGn1Threads) gn_onepass_kernel(const GnArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------- group-owner GroupNorm
+// Small / mid-size activations (the whole tensor is L2 resident: every UNet level at batch <= 8): one CTA owns ONE
+// (sample, group) — its HW x cpg elements — so the statistics need no exchange between CTAs at all: no cluster, no
+// DSMEM, no second kernel.  NB x 32 CTAs (256 at batch 4) fill the machine where a cluster per sample used 64 SMs.  The
+// group's elements are short channel runs (cpg * 2 bytes per pixel, e.g. 20 B at 320 channels) strided by the pixel
+// pitch; the neighbouring groups' CTAs run at the same time, so the partially used sectors are shared through L2.
+// The slab is kept in shared memory between the statistics and the apply pass when it fits (else re-read from L2).
+// Deterministic: fixed thread -> element mapping, shuffle tree, fp64 fold of the per-warp sums in warp order.
+constexpr int kGgThreads = 480;   // a multiple of every vectors-per-pixel count in use (5, 10, 15, 2, 4, 8, ...): see below
+constexpr int kGgMaxCpg = 128;
+constexpr int kGgSlabBudget = 200 * 1024;
+
+template <typename V>   // uint32_t / uint2 / uint4 = 2 / 4 / 8 channels per vector
+__global__ void __launch_bounds__(kGgThreads, 2) gn_group_kernel(const GnArgs a, const int nvec, const int use_smem) {
+  griddep_launch();
+  constexpr int VW = static_cast<int>(sizeof(V)) / 2;
+  constexpr int U = sizeof(V) == 16 ? 4 : 8;   // independent loads in flight per thread
+  extern __shared__ __align__(16) uint8_t ggs[];
+  __shared__ double s_ws[kGgThreads / 32][2];
+  __shared__ float s_stat[2];
+  V* slab = reinterpret_cast<V*>(ggs);
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int cpg = a.C / a.groups;
+  // 480 % nvec == 0: a thread always handles the same vector slot j of its pixels (pixels pl, pl + ppi, ...), so its
+  // affine coefficients live in registers and the addresses advance by a constant
+  const int ppi = kGgThreads / nvec;
+  const int pl = static_cast<int>(threadIdx.x) / nvec, j = static_cast<int>(threadIdx.x) - pl * nvec;
+  const int c = g * cpg + j * VW;
+  const bool first = c < a.C0;
+  const size_t pitch = first ? a.C0 : a.C1;
+  const __half* src = (first ? a.x0 + c : a.x1 + (c - a.C0)) + (static_cast<size_t>(n) * a.HW + pl) * pitch;
+  const size_t step = static_cast<size_t>(ppi) * pitch;
+  const int niter = pl < a.HW ? (a.HW - pl + ppi - 1) / ppi : 0;
+  griddep_wait();
+
+  float sum = 0.0f, sq = 0.0f;
+  for (int it = 0; it < niter; it += U) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (it + u < niter) v[u] = __ldg(reinterpret_cast<const V*>(src + (it + u) * step));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (it + u < niter) {
+        if (use_smem) slab[(it + u) * kGgThreads + threadIdx.x] = v[u];
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < VW / 2; ++k) {
+          const float2 f = __half22float2(h[k]);
+          sum += f.x + f.y;
+          sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
+        }
+      }
+    }
+  }
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) {
+    s_ws[threadIdx.x >> 5][0] = static_cast<double>(sum);
+    s_ws[threadIdx.x >> 5][1] = static_cast<double>(sq);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ds = 0.0, dq = 0.0;
+    for (int w = 0; w < kGgThreads / 32; ++w) {   // fixed order
+      ds += s_ws[w][0];
+      dq += s_ws[w][1];
+    }
+    const double cnt = static_cast<double>(a.HW) * cpg;
+    const double mean = ds / cnt;
+    double var = dq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_stat[0] = static_cast<float>(mean);
+    s_stat[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  }
+  __syncthreads();
+  float A[VW], B[VW];
+  if (niter > 0) {
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      A[k] = s_stat[1] * __ldg(a.gamma + c + k);
+      B[k] = __ldg(a.beta + c + k) - s_stat[0] * A[k];
+    }
+  }
+  __half* dst = a.y + (static_cast<size_t>(n) * a.HW + pl) * a.C + c;
+  const size_t dstep = static_cast<size_t>(ppi) * a.C;
+  for (int it = 0; it < niter; it += U) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (it + u < niter)
+        v[u] = use_smem ? slab[(it + u) * kGgThreads + threadIdx.x] : __ldg(reinterpret_cast<const V*>(src + (it + u) * step));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (it + u < niter) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+        V o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int k = 0; k < VW / 2; ++k) {
+          const float2 f = __half22float2(h[k]);
+          float y0 = fmaf(f.x, A[2 * k], B[2 * k]), y1 = fmaf(f.y, A[2 * k + 1], B[2 * k + 1]);
+          if (a.silu) {
+            y0 = silu_tanh(y0);
+            y1 = silu_tanh(y1);
+          }
+          ow[k] = pack_half2(y0, y1);
+        }
+        *reinterpret_cast<V*>(dst + (it + u) * dstep) = o;
+      }
+    }
+  }
+}
+
+template <typename V>
+int launch_gn_group(const GnArgs& a, int vw, cudaStream_t st) {
+  const int cpg = a.C / a.groups;
+  const int nvec = cpg / vw;
+  const int ppi = kGgThreads / nvec;
+  // slab slots: ceil(HW / ppi) rounds of kGgThreads vectors
+  const size_t slab = static_cast<size_t>((a.HW + ppi - 1) / ppi) * kGgThreads * sizeof(V);
+  const int use_smem = slab <= static_cast<size_t>(kGgSlabBudget);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gn_group_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGgSlabBudget);
+    if (e != cudaSuccess) return udt_host::fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(gn group smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  udt_host::launch_pdl(gn_group_kernel<V>, dim3(a.groups, a.NB), dim3(kGgThreads), use_smem ? slab : 0, st, a, nvec, use_smem);
+  return udt_host::check_launch("udt_groupnorm_nhwc (group owner)");
+}
+
 constexpr int kGn1SlabBudget = 176 * 1024;   // + <= 32 KB of partial sums (<= 208 KB dynamic) + ~9 KB static < 227 KB
 
 // cluster size of the one-pass schedule for this problem, 0 = use the two-pass schedule
@@ -659,6 +791,26 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
       if (cudaOccupancyMaxActiveClusters(&nclusters, gn_onepass_kernel, &q) == cudaSuccess && nclusters >= 4) max_cluster = 16;
     }
     (void)cudaGetLastError();
+  }
+  // group-owner schedule while the whole tensor is L2 resident (UDT_GN_GROUP=0: never)
+  static const bool group_ok = [] {
+    const char* e = getenv("UDT_GN_GROUP");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  {
+    const int cpg = C / groups;
+    const size_t bytes = static_cast<size_t>(NB) * HW * C * 2;
+    const int vw = cpg % 8 == 0 ? 8 : (cpg % 4 == 0 ? 4 : 2);
+    // measured on B200 (batch 4): wins where a pixel contributes a run of >= 40 bytes and the slab fits shared memory twice per
+    // SM (32x32x640 13.2 -> 9.9 us, 16x16x1280 9.4 -> 5.0 us, 8x8x1280 7.1 -> 3.5 us); loses at 64x64x320 (20-byte runs:
+    // 19.5 -> 23.4 us), which keeps the two-pass schedule
+    const size_t slab = static_cast<size_t>(HW) * cpg * 2;
+    if (group_ok && cpg % 2 == 0 && cpg * 2 >= 40 && cpg <= kGgMaxCpg && kGgThreads % (cpg / vw) == 0 && slab <= 128 * 1024 &&
+        bytes <= (static_cast<size_t>(64) << 20)) {
+      if (vw == 8) return launch_gn_group<uint4>(a, 8, st);
+      if (vw == 4) return launch_gn_group<uint2>(a, 4, st);
+      return launch_gn_group<uint32_t>(a, 2, st);
+    }
   }
   const int S = onepass_ok ? gn_onepass_cluster(NB, HW, C, max_cluster) : 0;
   if (S > 0) {
