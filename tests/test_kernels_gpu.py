@@ -429,11 +429,13 @@ def test_linear_per_sample_rowbias(udt_lib):
                                                (3, 1024, 640, 0, True), (1, 1024, 320, 320, True), (5, 100, 64, 0, True),
                                                (2, 4096, 320, 0, True), (1, 37, 96, 32, False), (8, 4096, 640, 320, True),
                                                (8, 1024, 1280, 640, True), (64, 1024, 640, 0, True), (52, 256, 1280, 1280, True),
-                                               (1, 262144, 128, 0, True), (2, 65536, 256, 256, False)])
+                                               (1, 262144, 128, 0, True), (2, 65536, 256, 256, False),
+                                               (3, 1000, 320, 0, True), (2, 4096, 512, 0, False), (1, 3000, 320, 640, True),
+                                               (8, 4096, 320, 320, True)])
 def test_groupnorm_schedules(udt_lib, nb, hw, c0, c1, silu):
     """group-owner schedule (L2-resident tensors <= 64 MB: ragged pixel counts, two-source concat incl. a group that
-    straddles the two sources, slab in shared memory or re-read), and — for the last four, larger tensors — the one-pass
-    cluster schedule (sample fits a cluster) and the two-pass one (VAE resolutions, with the fold kernel)"""
+    straddles the two sources), the two-pass schedule (64x64 level: 320 / 640 / 960 channels, ragged pixel counts, VAE
+    resolutions with the fold kernel) and the one-pass cluster schedule (tensors above 64 MB whose sample fits a cluster)"""
     from udifftext_b200 import ops
     dev = _dev()
     g = torch.Generator().manual_seed(nb * hw + c0 + c1)
