@@ -1,6 +1,7 @@
 """A handful of representative launches for `ncu --set full` captures (one per kernel family, UNet shapes at batch 4).
 usage: python scripts/ncu_targets.py [which ...]   which in {linear, conv, fmha, ln, gn, xattn, conv8}"""
 import math
+import os
 import sys
 
 import torch
@@ -13,7 +14,7 @@ def main():
     which = sys.argv[1:] or ["linear", "conv", "fmha", "ln", "gn", "xattn", "conv8"]
     dev = torch.device("cuda", 0)
     nb = 8
-    reps = 3
+    reps = int(os.environ.get("UDT_NCU_REPS", "3"))
     if "linear" in which:
         m, k, n = nb * 4096, 320, 320
         x = torch.randn((m, k), device=dev).half()
@@ -53,7 +54,7 @@ def main():
             ops.layernorm(x, g, g, 1e-5)
     if "gn" in which:
         g = torch.ones(1280, device=dev)
-        for hw, c in ((4096, 320), (64, 1280)):
+        for hw, c in ((4096, 320), (1024, 640), (64, 1280)):   # two-pass, group-owner, group-owner
             x = torch.randn((nb, hw, c), device=dev).half()
             for _ in range(reps):
                 ops.groupnorm(x, g[:c], g[:c], 1e-5, True)

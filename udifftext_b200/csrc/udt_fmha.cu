@@ -57,6 +57,18 @@ struct FmhaParams {
   int32_t pairs_full;     // (b * heads + h) * pairs_per_bh + pair; the CTAs after them own ONE tile of the remaining pairs
 };
 
+// 2^x on the FMA / ALU pipes (the MUFU pipe, 16 ex2/clk/SM, is the busiest pipe of this kernel: 66 % under ncu): round-to-
+// nearest split x = j + f by the 1.5 * 2^23 trick, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error
+// 7.5e-5, well below the fp16 rounding of P, 4.9e-4), j added into the exponent field.  x is clamped to [-126, 126]: below,
+// the result is ~2^-126 ~ 0; above, it is huge and trips the row-sum bound exactly like the MUFU result (+inf) would.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fminf(fmaxf(x, -126.0f), 126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  const float p = fmaf(fmaf(fmaf(0.055171654f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+
 // Work of this CTA.  The grid is linear: whole waves of tile pairs first, then — when the last, partial wave would leave
 // more than half of the SMs idle — its pairs as twice as many single-tile CTAs (a single-tile CTA has the exp pipe and
 // the TMEM read port to itself and finishes in ~0.55 of a pair's time, so the tail wave shrinks accordingly).
@@ -393,6 +405,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_cons
   }
 }
 
+// kPoly > 0: every kPoly-th exponential of the single-pass path is evaluated by ex2_poly instead of MUFU.EX2
+template <int kPoly>
 __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_constant__ FmhaParams p) {
   griddep_launch();   // PDL: let the next kernel's prologue start
   extern __shared__ uint8_t smem_raw[];
@@ -570,8 +584,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
               float p0 = fmaf(__uint_as_float(vv[i]), sl2, -m_ref);
               float p1 = fmaf(__uint_as_float(vv[i + 1]), sl2, -m_ref);
               if (!UDT_FDBG(1)) {
-                p0 = ex2_approx(p0);
-                p1 = ex2_approx(p1);
+                p0 = (kPoly > 0 && (i % kPoly) == kPoly - 1) ? ex2_poly(p0) : ex2_approx(p0);
+                p1 = (kPoly > 0 && ((i + 1) % kPoly) == kPoly - 1) ? ex2_poly(p1) : ex2_approx(p1);
               }
               rowsum += p0 + p1;
               pk[i >> 1] = pack_half2(p0, p1);
@@ -722,13 +736,17 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   // P kept in TMEM (TS-form PV MMA) is the production schedule; UDT_FMHA_TS=0 selects the smem-P kernel for A/B measurements
   static const int use_ts = [] { const char* e = getenv("UDT_FMHA_TS"); return e ? atoi(e) : 1; }();
   if (use_ts) {
+    // experiment switch: UDT_FMHA_POLY=4 moves every 4th exponential from MUFU to the FMA pipe.  Measured on B200: no gain
+    // (4096 tokens 249.0 -> 250.4 us; every 2nd: 275 us) — the kernel is bound by the TMEM read path, not by MUFU
+    static const int poly = [] { const char* e = getenv("UDT_FMHA_POLY"); return e ? atoi(e) : 0; }();
+    void (*kern)(FmhaParams) = poly == 0 ? udt_fmha_ts_kernel<0> : udt_fmha_ts_kernel<4>;
     static bool ts_attr = false;
     if (!ts_attr) {
-      cudaError_t e = cudaFuncSetAttribute(udt_fmha_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
       if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha ts smem): %s", cudaGetErrorString(e));
       ts_attr = true;
     }
-    udt_host::launch_pdl(udt_fmha_ts_kernel, dim3(grid), dim3(kThreads), kTsSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
+    udt_host::launch_pdl(kern, dim3(grid), dim3(kThreads), kTsSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("udt_fmha_fwd (ts)");
   }
   udt_host::launch_pdl(udt_fmha_kernel, dim3(grid), dim3(kThreads), kSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
