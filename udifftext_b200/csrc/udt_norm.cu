@@ -797,6 +797,10 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
     const char* e = getenv("UDT_GN_GROUP");
     return e == nullptr || atoi(e) != 0;
   }();
+  static const size_t group_limit = [] {      // tensor size up to which the group-owner schedule is used (UDT_GN_GROUP_MB)
+    const char* e = getenv("UDT_GN_GROUP_MB");
+    return static_cast<size_t>(e ? atoi(e) : 64) << 20;
+  }();
   {
     const int cpg = C / groups;
     const size_t bytes = static_cast<size_t>(NB) * HW * C * 2;
@@ -806,7 +810,7 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
     // 19.5 -> 23.4 us), which keeps the two-pass schedule
     const size_t slab = static_cast<size_t>(HW) * cpg * 2;
     if (group_ok && cpg % 2 == 0 && cpg * 2 >= 40 && cpg <= kGgMaxCpg && kGgThreads % (cpg / vw) == 0 && slab <= 128 * 1024 &&
-        bytes <= (static_cast<size_t>(64) << 20)) {
+        bytes <= group_limit) {
       if (vw == 8) return launch_gn_group<uint4>(a, 8, st);
       if (vw == 4) return launch_gn_group<uint2>(a, 4, st);
       return launch_gn_group<uint32_t>(a, 2, st);
