@@ -90,3 +90,30 @@ def test_uc_cross_attention_shortcut_is_exact(udt_lib):
     err = _rel(y_skip, y_full)
     print("uc shortcut vs full rel-L2:", err)
     assert err < 2e-3   # identical in real arithmetic; one fp16 rounding fewer on the uc residual stream
+
+
+def test_measured_igemm_tiles_do_not_change_results(udt_lib):
+    """udifftext_b200/tuning/igemm_bn_b200.json (scripts/tune_igemm_bn.py) only overrides the column tile of udt_igemm:
+    the batch-4 UNet evaluation with the table must agree with the library's own tile choice to fp16 rounding"""
+    from udifftext_b200 import ops, synth
+    from udifftext_b200.unet import UNetB200
+    dev = torch.device("cuda", 0)
+    unet = UNetB200(_unet_sd("full"), dev, **synth.ARCH["full"]["unet"])
+    g = torch.Generator().manual_seed(3)
+    nb = 8
+    x = torch.randn((nb, 9, 64, 64), generator=g).to(dev)
+    t = torch.tensor([999, 700, 500, 300, 200, 100, 50, 19], device=dev)
+    ctx = torch.randn((nb, 12, 2048), generator=g).to(dev)
+    saved = ops.IGEMM_TUNING
+    try:
+        ops.IGEMM_TUNING = None
+        table = dict(ops._igemm_tuning())
+        y_tuned = unet.forward(x, t, ctx).float().clone()
+        ops.IGEMM_TUNING = {}
+        y_model = unet.forward(x, t, ctx).float().clone()
+    finally:
+        ops.IGEMM_TUNING = saved
+    torch.cuda.synchronize()
+    rel = ((y_tuned - y_model).norm() / y_model.norm()).item()
+    print(f"igemm tile table: {len(table)} entries, tuned vs cost-model UNet output rel-L2 {rel:.2e}")
+    assert torch.isfinite(y_tuned).all() and rel < 2e-3

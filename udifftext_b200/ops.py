@@ -19,6 +19,21 @@ _launches = 0   # C-ABI compute calls issued by this process (each is one or two
 SHAPE_LOG = None  # when a list: one problem-shape tuple per call (scripts/profile_unet_step.py)
 _prof = None    # when a list: (entry point, start event, end event) per call — see profile_step()
 CALL_LOG = None  # when a list: (entry point, bound function, args, shape) per call, for scripts/profile_step_graph.py
+KEY_LOG = None   # when a list: the tuning key of every udt_igemm call (scripts/tune_igemm_bn.py)
+IGEMM_TUNING = None   # {problem key: column tile}: measured exceptions to the library's cost model (udifftext_b200/tuning/)
+
+
+def _igemm_tuning() -> dict:
+    """lazily load the measured BN table (scripts/tune_igemm_bn.py); UDT_IGEMM_TUNING=0 ignores it"""
+    global IGEMM_TUNING
+    if IGEMM_TUNING is None:
+        IGEMM_TUNING = {}
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning", "igemm_bn_b200.json")
+        if os.environ.get("UDT_IGEMM_TUNING", "1") != "0" and os.path.exists(path):
+            import json
+            with open(path) as f:
+                IGEMM_TUNING = json.load(f)
+    return IGEMM_TUNING
 
 
 def launch_count() -> int:
@@ -196,6 +211,16 @@ def igemm(
         d.out_stride_w, d.out_stride_h, d.out_stride_n = out_strides
     ws = _splitk_ws(out.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    tuning = _igemm_tuning()
+    if bn_hint == 0 and (tuning or KEY_LOG is not None):
+        key = "|".join([f"{nb}x{h}x{w}", str(n_out), "+".join(f"{src[3]}x{src[1]}s{src[4] if len(src) > 4 else 1}" for src in srcs),
+                        str(act), "r" if residual is not None else "-", "b" if rowbias is not None else "-",
+                        "f32" if out_fp32 else "f16", "v" if out_strides is not None else "-", str(weight_img_rows)])
+        if KEY_LOG is not None:
+            KEY_LOG.append(key)
+        d.bn_hint = tuning.get(key, 0)
+    elif KEY_LOG is not None:
+        KEY_LOG.append("fixed")
     if SHAPE_LOG is not None:
         k = sum(src[3] * ((src[1] + 63) // 64 * 64) for src in srcs)
         tag = "+".join(f"{src[3]}x{src[1]}" + (f"s{src[4]}" if len(src) > 4 and src[4] != 1 else "") for src in srcs)
