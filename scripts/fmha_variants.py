@@ -1,4 +1,4 @@
-"""FMHA variant check (run once per UDT_FMHA_TS setting): accuracy incl. large score spreads and ragged key tiles, then timing."""
+"""FMHA variant check (run once per UDT_FMHA_TS / UDT_FMHA_POLY / UDT_FMHA_TAIL setting): accuracy incl. large score spreads and ragged key tiles, then timing."""
 import json, os, sys, torch
 sys.path.insert(0, ".")
 from udifftext_b200 import ops

@@ -330,7 +330,7 @@ def test_vae_sample_pack_and_pointwise_affine(udt_lib):
     torch.cuda.synchronize()
     assert torch.equal(cat_c, again_c) and torch.equal(cat_uc, again_uc), "K10 is not deterministic"
     # fp64 reference (the fp32 CPU evaluation was seen to disagree once in a while on a cold box; 400 back-to-back launches of
-    # the kernel are bit-identical and within 2.4e-7 of it — scripts/_k10_stress.py)
+    # the kernel are bit-identical and within 2.4e-7 of it — scripts/k10_stress.py)
     m8 = F.interpolate(mask.double(), scale_factor=0.125, mode="bilinear")
     ref_c = torch.cat([m8, 0.18215 * R.posterior_sample(moments.double(), n_c.double())], dim=1)
     ref_uc = torch.cat([m8, 0.18215 * R.posterior_sample(moments.double(), n_uc.double())], dim=1)
