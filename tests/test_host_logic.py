@@ -232,3 +232,34 @@ def test_host_schedule_equals_unmodified_reference_classes():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "equal" in out.stdout
+
+
+def test_init_from_ckpt_round_trip(tmp_path):
+    """DiffusionEngine.init_from_ckpt (diffusion.py:87-105): the reference's Lightning `.ckpt` ({"state_dict": ...}) and
+    `.safetensors` layouts load with the reference's key names; strict=False tolerates missing / unexpected keys"""
+    from udifftext_b200 import api, synth
+    sd = synth.synthetic_state_dict(synth.load_manifest("tiny"), 77)
+    ckpt = tmp_path / "model.ckpt"
+    torch.save({"state_dict": dict(sd, **{"model_ema.decay": torch.tensor(0.999)}), "global_step": 1}, ckpt)
+    eng = api.build_engine("tiny", seed=1)                       # different weights
+    eng.init_from_ckpt(str(ckpt))
+    got = eng.state_dict()
+    assert set(sd) <= set(got)
+    for k, v in sd.items():
+        assert torch.equal(got[k].cpu().to(v.dtype), v), k
+    try:
+        from safetensors.torch import save_file
+    except ImportError:
+        pytest.skip("safetensors not installed")
+    part = {k: v.contiguous() for k, v in sd.items() if k.startswith("model.diffusion_model.")}   # partial file: UNet only
+    st = tmp_path / "unet.safetensors"
+    save_file(part, str(st))
+    eng2 = api.build_engine("tiny", seed=2)
+    before = {k: v.clone() for k, v in eng2.state_dict().items()}
+    eng2.init_from_ckpt(str(st))
+    after = eng2.state_dict()
+    for k in sd:
+        want = sd[k] if k in part else before[k]
+        assert torch.equal(after[k].cpu().to(want.dtype), want.cpu()), k
+    with pytest.raises(NotImplementedError):
+        eng2.init_from_ckpt(str(tmp_path / "weights.bin"))
