@@ -10,7 +10,7 @@ inference (`embedder.train = disabled_train` is installed before `model.eval()`,
 util.py:18-20), so dropout(p=0.1) makes the text embedding random.  Golden vectors are generated with the
 LabelEncoder switched to eval mode (`nn.Module.train(le, False)`) — the deterministic function both sides share.
 
-usage: python oracle/make_golden.py [tiny] [loss] [full_unet] [c1]
+usage: python oracle/make_golden.py [tiny] [loss] [noise_search] [full_unet] [c1]
 """
 import os
 import sys
@@ -153,6 +153,67 @@ def gen_loss():
                os.path.join(GOLD, "loss.pt"))
 
 
+class _CpuDeviceTorch:
+    """stand-in for the `torch` global of sgm/modules/diffusionmodules/sampling.py while get_init_noise runs: the function
+    hard-codes torch.device("cuda", index=cfgs.gpu) (sampling.py:269,311); every other attribute is the real torch"""
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def device(*args, **kwargs):
+        return torch.device("cpu")
+
+
+def gen_noise_search():
+    """the reference's EulerEDMSampler.get_init_noise (sampling.py:264-322) UNMODIFIED on CPU for one image (the case it
+    supports), 3 trial noises; the per-trial scores are recorded by wrapping loss_fn.get_min_local_loss"""
+    import types
+    m, sd = reference_engine("tiny")                     # imports the reference (shims installed)
+    import sgm.modules.diffusionmodules.sampling as S
+    sampler = S.EulerEDMSampler(num_steps=4, guider_config={
+        "target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": 5.0}}, **SAMPLER_CFG)
+    batch = synth.synthetic_batch(102, 1, 64, 64, 5)
+    batch_uc = dict(batch, txt=[""], label=[""])
+    iters = 3
+    cfgs = types.SimpleNamespace(batch_size=1, channel=4, factor=8, noise_iters=iters, gpu=0)
+    m.loss_fn.min_attn_size = 4          # configuration (loss_fn_config.params.min_attn_size): the tiny maps are 8x8 and 4x4
+    scores = []
+    orig = m.loss_fn.get_min_local_loss
+
+    def recording(*a, **k):
+        out = orig(*a, **k)
+        scores.append(out.detach().clone())
+        return out
+
+    m.loss_fn.get_min_local_loss = recording
+    real_torch = S.torch
+    torch.manual_seed(2102)
+    with torch.no_grad():
+        c, uc = m.conditioner.get_unconditional_conditioning(batch, batch_uc=batch_uc, force_uc_zero_embeddings=["label"])
+        state = torch.get_rng_state()
+        S.torch = _CpuDeviceTorch()
+        try:
+            best = sampler.get_init_noise(cfgs, m, c, batch, uc)
+        finally:
+            S.torch = real_torch
+            m.loss_fn.get_min_local_loss = orig
+    assert len(scores) == 2 * iters                       # one score per sampler step, two steps per trial
+    last = torch.stack([s_[s_.shape[0] // 2:] for s_ in scores[1::2]])          # [iters, 1]: conditional half, last step
+    torch.set_rng_state(state)
+    noises = [torch.randn((1, 4, 8, 8)) for _ in range(iters)]
+    lf = m.loss_fn
+    with torch.no_grad():
+        mine_best, mine_losses = R.init_noise_search(R._sub(sd, "model.diffusion_model."), noises, c, uc, batch["mask"],
+                                                     batch["seg_mask"], 5.0, lf.gaussian_kernel_size, 1.0, lf.min_attn_size)
+    print("noise search: reference scores", last.flatten().tolist(), "restated", mine_losses.flatten().tolist())
+    assert torch.allclose(mine_losses, last, atol=1e-5) and torch.equal(mine_best, best)
+    torch.save({"config_id": 102, "label_len": 5, "seed": 2102, "iters": iters, "scale": 5.0, "noises": noises, "best": best,
+                "losses": last, "c_concat": c["concat"], "uc_concat": uc["concat"], "c_crossattn": c["t_crossattn"],
+                "uc_crossattn": uc["t_crossattn"], "kernel_size": lf.gaussian_kernel_size, "sigma": 1.0,
+                "min_attn_size": lf.min_attn_size}, os.path.join(GOLD, "noise_search.pt"))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["tiny"]
     os.makedirs(GOLD, exist_ok=True)
@@ -160,6 +221,8 @@ if __name__ == "__main__":
         gen_tiny()
     if "loss" in what:
         gen_loss()
+    if "noise_search" in what:
+        gen_noise_search()
     m = sd = None
     if "full_unet" in what:
         m, sd = gen_full_unet()

@@ -393,9 +393,9 @@ def init_noise_search(unet_sd: SD, noises: Sequence[torch.Tensor], c: dict, uc: 
     """sampling.py:264-322 get_init_noise: every trial noise is sampled for 2 steps (prepare_sampling_loop num_steps=2),
     scored by get_min_local_loss on the attention maps of the LAST step (conditional half, sampling.py:340-341) and the
     lowest score wins (first one on ties: stable sort).  The reference scores one image (`.item()`); here every image keeps
-    its own winner.  Returns (best noise [B,4,h,w], losses [iters, B]).  The reference function itself hard-codes a cuda
-    device (sampling.py:269,311) and cannot run in the build container: this composition is unpinned as a whole, its parts
-    (cfg_denoise_eps + exported maps: tests/golden/tiny.pt; min_local_loss: tests/golden/loss.pt) are pinned."""
+    its own winner.  Returns (best noise [B,4,h,w], losses [iters, B]).  Pinned for one image against the UNMODIFIED
+    reference function run on CPU (its hard-coded cuda device, sampling.py:269,311, redirected by a stand-in `torch` global):
+    oracle/make_golden.py noise_search -> tests/golden/noise_search.pt (scores agree to 1e-8, same winning noise)."""
     sig = sampler_sigmas(2)
     table = denoiser_sigmas()
     losses = []

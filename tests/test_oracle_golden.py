@@ -86,3 +86,20 @@ def test_oracle_min_local_loss_matches_reference_golden():
     got = R.min_local_loss(gold["cache"], gold["mask"], gold["seg_mask"], gold["kernel_size"], gold["sigma"], gold["min_attn_size"])
     assert torch.allclose(got, gold["loss"], atol=1e-7)
     assert gold["loss"].abs().min() > 1e-3   # not vacuous: the masked region carries attention
+
+
+def test_oracle_noise_search_matches_reference_golden(tiny_sd):
+    """get_init_noise (sampling.py:264-322) restated vs the unmodified reference function's trial scores and winner"""
+    from oracle import restated as R
+    gold = torch.load(os.path.join(GOLD, "noise_search.pt"))
+    from udifftext_b200 import synth
+    batch = synth.synthetic_batch(gold["config_id"], 1, 64, 64, gold["label_len"])
+    c = {"concat": gold["c_concat"], "t_crossattn": gold["c_crossattn"]}
+    uc = {"concat": gold["uc_concat"], "t_crossattn": gold["uc_crossattn"]}
+    with torch.no_grad():
+        best, losses = R.init_noise_search(R._sub(tiny_sd, "model.diffusion_model."), gold["noises"], c, uc, batch["mask"],
+                                           batch["seg_mask"], gold["scale"], gold["kernel_size"], gold["sigma"],
+                                           gold["min_attn_size"])
+    assert torch.allclose(losses, gold["losses"], atol=1e-5)
+    assert torch.equal(best, gold["best"])
+    assert (gold["losses"].max() - gold["losses"].min()).item() > 1e-3      # the trials are distinguishable

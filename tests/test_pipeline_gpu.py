@@ -180,3 +180,27 @@ def test_noise_search_matches_oracle(tiny_engine, b):
     for j in range(b):
         if (gaps[1, j] - gaps[0, j]).item() > 4 * err:        # a clear winner: the same noise must be kept
             assert torch.equal(best[j], ref_best[j])
+
+
+def test_noise_search_matches_reference_golden(tiny_engine):
+    """product get_init_noise (noise_iters = 3, one image) vs the unmodified reference's run (tests/golden/noise_search.pt):
+    same RNG draw order (conditioner posterior draws, then one noise per trial + one spare), same winner, scores within
+    fp16 tolerance"""
+    from udifftext_b200 import api, synth
+    gold = torch.load(os.path.join(GOLD, "noise_search.pt"))
+    cfgs = api.runtime_config(steps=4, batch_size=1, noise_iters=gold["iters"], scale=[gold["scale"], 0.0])
+    sampler = api.init_sampling(cfgs)
+    batch = synth.synthetic_batch(gold["config_id"], 1, 64, 64, gold["label_len"])
+    torch.manual_seed(gold["seed"])
+    with torch.no_grad():
+        dbatch, dbatch_uc = api.prepare_batch(cfgs, dict(batch))
+        c, uc = tiny_engine.conditioner.get_unconditional_conditioning(dbatch, batch_uc=dbatch_uc,
+                                                                      force_uc_zero_embeddings=["label"])
+        best = sampler.get_init_noise(cfgs, tiny_engine, cond=c, batch=dbatch, uc=uc)
+    torch.cuda.synchronize()
+    assert _rel(c["concat"], gold["c_concat"]) < 2e-3
+    got = sampler.last_init_losses.cpu()
+    err = (got - gold["losses"]).abs().max().item()
+    print(f"noise search vs reference: scores {got.flatten().tolist()} vs {gold['losses'].flatten().tolist()} (max abs err {err:.2e})")
+    assert err < 1e-2 * gold["losses"].abs().max().item() + 2e-4
+    assert torch.equal(best.cpu(), gold["best"])          # trial scores differ by > 2e-3: the winner is unambiguous
