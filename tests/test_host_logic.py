@@ -263,3 +263,17 @@ def test_init_from_ckpt_round_trip(tmp_path):
         assert torch.equal(after[k].cpu().to(want.dtype), want.cpu()), k
     with pytest.raises(NotImplementedError):
         eng2.init_from_ckpt(str(tmp_path / "weights.bin"))
+
+
+def test_request_batch_u8_validates_its_inputs():
+    """demo.py:52-98 front-end: malformed requests are rejected before anything touches the device"""
+    import numpy as np
+    from udifftext_b200 import api
+    cfgs = api.runtime_config(batch_size=2, H=64, W=64, seq_len=12)
+    img = np.zeros((64, 64, 3), dtype=np.uint8)
+    with pytest.raises(ValueError):
+        api.request_batch_u8(cfgs, img.astype(np.float32), img, "abc", 2)          # not uint8
+    with pytest.raises(ValueError):
+        api.request_batch_u8(cfgs, img, np.zeros((32, 64, 3), dtype=np.uint8), "abc", 2)   # mask of another size
+    with pytest.raises(ValueError):
+        api.request_batch_u8(cfgs, img, img, "x" * 13, 2)                            # longer than seq_len
