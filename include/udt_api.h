@@ -32,7 +32,7 @@ extern "C" {
 #define UDT_ACT_GEGLU 2 /* out[:, j] = x_j * gelu_erf(gate_j); weight rows interleaved per column tile */
 #define UDT_ACT_RELU 3
 
-int udt_version(void);            /* ABI version (4: + udt_attn_local_score, udt_request_pack_u8, udt_images_to_u8) */
+int udt_version(void);            /* ABI version (5: udt_cfg_euler_step takes cfg_scale_dev; fp32-stream LabelEncoder entry points) */
 int udt_arch(void);               /* compute capability of the current device *10 (100 on B200); <0 on error */
 const char* udt_last_error(void); /* thread-local message of the last failing call */
 int udt_num_sms(void);
@@ -149,8 +149,22 @@ int udt_attn_local_score(const float* probs, const float* mask, const float* seg
  * the multi-head self-attention of its nn.TransformerEncoder layers over the fused in_proj output
  * qkv fp16 [B*L, ld >= 3*heads*dh] (q | k | v), L <= 16 tokens, head dim <= 256, no mask:
  * o fp16 [B*L, ldo] = softmax(q k^T * scale) v per head.  The projections / FFN run through udt_igemm. */
-int udt_label_embed(const int32_t* idx, const float* emb, const float* pe, void* out, int32_t rows, int32_t L,
-                    int32_t D, void* stream);
+int udt_label_embed(const int32_t* idx, const float* emb, const float* pe, void* out, float* out_f32 /* NULL or fp32 [rows, D] */,
+                    void* out_lo /* NULL or fp16 [rows, D]: rn(v - rn(v)), the low half of the fp16 pair */, int32_t rows,
+                    int32_t L, int32_t D, void* stream);
+/* fp32-stream evaluation of the LabelEncoder: its output conditions every sampler step of a request, so its rounding error
+ * is systematic (it does not average out over the steps like the UNet's activation rounding).  The encoder is tiny
+ * (7 GFLOP per string), so its residual stream stays fp32 and every GEMM operand is an fp16 PAIR hi + lo
+ * (x ~= hi + lo to 2^-22): x W^T ~= hi Wh^T + lo Wh^T + hi Wl^T on the same tensor-core kernel (udt_igemm, fp32 out).
+ *   udt_rowsum_norm_split: y[r, :] = LN( relu?( in0 + in1 + in2 ) + res )  (in1 / in2 / res / the LN (gamma = beta = NULL) are
+ *     optional) -> out_f32 and / or the pair out_hi / out_lo; the post-LN `x = norm(x + sublayer(x))` of
+ *     nn.TransformerEncoderLayer (encoders/modules.py:1103-1104) and the partial-product sums of the pair GEMMs.
+ *   udt_mha_small_f32: udt_mha_small on fp32 q | k | v, output as the pair o_hi / o_lo. */
+int udt_rowsum_norm_split(const float* in0, const float* in1, const float* in2, const float* res, int32_t rows, int32_t C,
+                          const float* gamma, const float* beta, float eps, int32_t relu, float* out_f32, void* out_hi,
+                          void* out_lo, void* stream);
+int udt_mha_small_f32(const float* qkv, void* o_hi, void* o_lo, int32_t B, int32_t L, int32_t heads, int32_t dh, int32_t ld,
+                      int32_t ldo, float scale, void* stream);
 int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int32_t heads, int32_t dh, int32_t ld, int32_t ldo,
                   float scale, void* stream);
 
@@ -177,11 +191,13 @@ int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld, float scal
  * fp32 NCHW [B,5,HW]; the UNet side is NHWC.  The per-step scalars live in device memory (`c_in_dev`,
  * `dsigma_dev` point at one fp32 each) so that one captured CUDA graph serves every step.
  *  pack:  unet_in[2B,HW,16] fp16 <- cat(x * c_in, concat_{uc|c}) zero padded to 16 channels (uc half first)
- *  step:  eps = eps_u + scale*(eps_c - eps_u); x += (sigma_next - sigma) * eps;  eps2b fp32 NHWC [2B,HW,4]   */
+ *  step:  eps = eps_u + scale*(eps_c - eps_u); x += (sigma_next - sigma) * eps;  eps2b fp32 NHWC [2B,HW,4]
+ *         (`cfg_scale_dev` != NULL: the guidance scale is read from device memory too, so a captured graph serves every
+ *          request whatever scale its guider carries)   */
 int udt_cfg_pack(const float* x, const float* concat_uc, const float* concat_c, void* unet_in, int32_t B, int32_t HW,
                  const float* c_in_dev, void* stream);
 int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32_t HW, float cfg_scale, const float* dsigma_dev,
-                       void* stream);
+                       const float* cfg_scale_dev /* NULL, or one fp32 on the device that overrides cfg_scale */, void* stream);
 
 /* K10 — conditioner tail (encoders/modules.py:843-857,1011-1014,195-198; distributions.py:24-41):
  * concat_{c,uc} fp32 NCHW [B,5,h*w] = cat(bilinear_1/8(mask), scale_factor * (mean + exp(0.5*clamp(logvar,-30,20)) * noise_{c,uc}))

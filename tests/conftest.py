@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # every fp32 oracle / torch reference evaluated on the GPU is TRUE fp32: TF32 has fp16's 10-bit mantissa, an oracle
+    # computed with it carries an error of the size the parity tests measure
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope="session")

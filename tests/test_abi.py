@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(udt_lib):
 
 def test_descriptor_layout_and_constants(udt_lib):
     from udifftext_b200 import lib, pack
-    assert udt_lib.udt_version() == 4
+    assert udt_lib.udt_version() == 5
     assert udt_lib.udt_sizeof_igemm_desc() == ctypes.sizeof(lib.IGemmDesc)
     assert udt_lib.udt_geglu_tile() == pack.GEGLU_TILE
 

@@ -632,3 +632,66 @@ def test_images_to_u8_is_bit_exact(udt_lib):
     got = ops.images_to_u8(x.to(dev))
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("rows,c,nparts,ln,relu,res", [(48, 2048, 3, True, False, True), (24, 2048, 3, False, True, False),
+                                                       (7, 6144, 3, False, False, False), (5, 128, 1, True, False, False)])
+def test_rowsum_norm_split_matches_torch(udt_lib, rows, c, nparts, ln, relu, res):
+    """fp32-stream LabelEncoder glue: y = LN(relu?(sum parts) + res) -> fp32 and the fp16 pair hi + lo (hi + lo = y to 2^-21)"""
+    from udifftext_b200 import ops
+    g = torch.Generator().manual_seed(rows + c)
+    parts = [torch.randn((rows, c), generator=g).cuda() for _ in range(nparts)]
+    r = torch.randn((rows, c), generator=g).cuda() if res else None
+    gamma = (1 + 0.1 * torch.randn(c, generator=g)).cuda() if ln else None
+    beta = (0.1 * torch.randn(c, generator=g)).cuda() if ln else None
+    y32 = torch.empty((rows, c), device="cuda")
+    hi, lo = torch.empty((rows, c), device="cuda", dtype=torch.float16), torch.empty((rows, c), device="cuda", dtype=torch.float16)
+    ops.rowsum_norm_split(parts, res=r, gamma=gamma, beta=beta, relu=relu, out_f32=y32, out_hi=hi, out_lo=lo)
+    ref = sum(p.double() for p in parts)
+    if relu:
+        ref = ref.clamp_min(0)
+    if res:
+        ref = ref + r.double()
+    if ln:
+        ref = torch.nn.functional.layer_norm(ref, (c,), gamma.double(), beta.double(), 1e-5)
+    assert _rel(y32, ref) < 2e-6
+    assert _rel(hi.double() + lo.double(), ref) < 2e-6
+    assert torch.equal(hi, y32.half())
+
+
+@pytest.mark.parametrize("b,l,heads,dh", [(4, 12, 8, 256), (2, 12, 8, 16), (3, 16, 4, 64), (1, 5, 2, 32)])
+def test_mha_small_f32_matches_torch(udt_lib, b, l, heads, dh):
+    from udifftext_b200 import ops
+    g = torch.Generator().manual_seed(b * 100 + l)
+    d = heads * dh
+    qkv = torch.randn((b * l, 3 * d), generator=g).cuda()
+    hi, lo = (torch.empty((b * l, d), device="cuda", dtype=torch.float16) for _ in range(2))
+    ops.mha_small_f32(qkv, b, l, heads, hi, lo)
+    q, k, v = (t.reshape(b, l, heads, dh).permute(0, 2, 1, 3).double() for t in qkv.chunk(3, dim=-1))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(b * l, d)
+    assert _rel(hi.double() + lo.double(), ref) < 5e-6
+
+
+def test_label_encoder_full_size_is_fp32_accurate(udt_lib):
+    """LabelEncoder at its real size (d = 2048, 12 layers) against the fp32 oracle: fp32 residual stream + fp16 operand pairs
+    keep the conditioning of every sampler step at fp32-level accuracy (an fp16 stream measured 1.2e-3 here and was the
+    largest single term of the decoded-pixel error, profiles/parity_r02.json)"""
+    from oracle import restated as R
+    from udifftext_b200 import synth
+    from udifftext_b200.label import LabelEncoderB200
+    man = {k: v for k, v in synth.load_manifest("full").items() if k.startswith("conditioner.embedders.0.")}
+    sd = R._sub(synth.synthetic_state_dict(man, 1234), "conditioner.embedders.0.")
+    enc = LabelEncoderB200(sd, "cuda:0")
+    labels = ["Hello", "B200!", "a", "UDiffText_12"]
+    got = enc(labels)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = R.label_encoder({k: v.cuda() for k, v in sd.items()}, labels)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    e = _rel(got, ref)
+    print(f"LabelEncoder full size vs fp32 oracle: rel-L2 {e:.3e}")
+    assert tuple(got.shape) == (4, 12, 2048) and got.dtype == torch.float32
+    assert e < 2e-5

@@ -40,7 +40,7 @@ def test_c5_768px_matches_oracle(full_engine):
     ez, ep = _rel(z, ref_z), _rel(img, ref_img)
     print(f"C5-shape predict (768px, 3 steps): latents rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}")
     assert tuple(img.shape) == (2, 3, 768, 768) and torch.isfinite(img).all()
-    assert ez < 1e-2 and ep < 1e-2   # fp16 storage / fp32 accumulation vs fp32
+    assert ez < 2.4e-3 and ep < 1.6e-3   # 1.5 x measured on B200 (1.61e-3 / 1.04e-3 after only 3 steps, profiles/parity_r02.json)
 
 
 def test_c3_batch32_rows_are_shard_independent(full_engine):
@@ -66,7 +66,7 @@ def test_c3_batch32_rows_are_shard_independent(full_engine):
     torch.cuda.synchronize()
     e = _rel(z4, z32[8:12])
     print(f"C3-shape predict (batch 32, 2 steps): shard rows 8..12 vs full request latents rel-L2 {e:.3e}")
-    assert e < 5e-3
+    assert e < 2.4e-3   # 1.5 x measured (1.58e-3: different tile shapes / split-K choices at batch 64 vs 8)
     # oracle on the first four rows: same global RNG order (posterior c, posterior uc, init noise for the WHOLE request)
     batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
     torch.manual_seed(41)
@@ -78,4 +78,4 @@ def test_c3_batch32_rows_are_shard_independent(full_engine):
         zr = R.euler_sample(R._sub(sd_dev, "model.diffusion_model."), x0[:4].to(dev), c, uc, 2, 5.0)
     eo = _rel(z32[:4], zr)
     print(f"C3-shape predict: rows 0..4 vs fp32 oracle latents rel-L2 {eo:.3e}")
-    assert eo < 1e-2
+    assert eo < 2.6e-3   # 1.5 x measured (1.75e-3 after 2 steps)

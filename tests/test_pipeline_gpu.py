@@ -31,11 +31,11 @@ def test_tiny_conditioner_matches_reference(tiny_engine):
     c, uc = tiny_engine.conditioner.get_unconditional_conditioning(batch, batch_uc=batch_uc, force_uc_zero_embeddings=["label"])
     torch.cuda.synchronize()
     # the c and uc latents are two different posterior draws of the same moments, in this order
-    assert _rel(c["concat"], gold["c_concat"]) < 5e-3
-    assert _rel(uc["concat"], gold["uc_concat"]) < 5e-3
+    assert _rel(c["concat"], gold["c_concat"]) < 2.2e-3      # VAE encoder in fp16 storage: 1.5 x measured 1.44e-3
+    assert _rel(uc["concat"], gold["uc_concat"]) < 2.2e-3
     assert (c["concat"][:, 1:] - uc["concat"][:, 1:]).abs().max().item() > 1e-3
     assert torch.equal(c["concat"][:, :1], uc["concat"][:, :1])
-    assert _rel(c["t_crossattn"], gold["c_crossattn"]) < 5e-3
+    assert _rel(c["t_crossattn"], gold["c_crossattn"]) < 5e-5  # fp32-stream LabelEncoder (label.py)
     assert uc["t_crossattn"].abs().max().item() == 0.0
     # generic (unfused) conditioner path: same RNG stream, same values
     torch.manual_seed(gold["predict_seed"])
@@ -55,7 +55,8 @@ def test_tiny_predict_matches_reference(tiny_engine):
     torch.cuda.synchronize()
     ez, ep = _rel(z, gold["predict_z"]), _rel(img, gold["predict_pixels"])
     print(f"tiny predict: z rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}, max-abs {(img.cpu() - gold['predict_pixels']).abs().max():.3e}")
-    assert ez < 2e-2 and ep < 2e-2
+    assert ez < 3.3e-3 and ep < 1.7e-3      # 1.5 x measured on B200 (2.17e-3 / 1.11e-3; 3 steps of the tiny network:
+    # the oracle itself with fp16-rounded operands sits at 1.2e-3 here — scripts/parity_report.py)
     # a second request replays the captured CUDA graph: bit-identical
     torch.manual_seed(gold["predict_seed"])
     img2, z2 = api.predict(cfgs, tiny_engine, sampler, synth.synthetic_batch(gold["predict_config_id"], 2, 64, 64, None))
@@ -105,7 +106,8 @@ def test_c1_full_predict_matches_reference(udt_lib):
     torch.cuda.synchronize()
     ez, ep = _rel(z, gold["z"]), _rel(img, gold["pixels_f16"])
     print(f"C1 predict: z rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}, max-abs {(img.cpu() - gold['pixels_f16'].float()).abs().max():.3e}")
-    assert ez < 3e-2 and ep < 3e-2
+    assert ep <= 1.0e-3, ep          # north-star tolerance on decoded pixels (measured 9.2e-4 vs the fp16-stored golden)
+    assert ez < 2.1e-3               # 1.5 x measured 1.42e-3
 
 
 def test_request_batch_u8_matches_fp32_request(tiny_engine):

@@ -36,7 +36,7 @@ def test_tiny_unet_matches_reference_golden(udt_lib):
     torch.cuda.synchronize()
     err = _rel(y, gold["unet_out"])
     print("tiny unet rel-L2 vs reference golden:", err)
-    assert err < 5e-3  # fp16 activations/weights vs the reference's fp32
+    assert err < 2.7e-3  # fp16 storage vs the reference's fp32: 1.5 x the 1.80e-3 measured on B200 (profiles/parity_r02.json)
     # attn_map_cache semantics (openaimodel.py:542-557): same order, same shapes, probabilities match
     assert len(net.attn_map_cache) == len(gold["unet_probs"])
     for item, ref in zip(net.attn_map_cache, gold["unet_probs"]):
@@ -46,7 +46,7 @@ def test_tiny_unet_matches_reference_golden(udt_lib):
     sd_dev = {k: v.to(dev) for k, v in sd.items()}
     with torch.no_grad():
         o = R.unet_forward(sd_dev, gold["unet_x"].to(dev), gold["unet_t"].to(dev), gold["unet_ctx"].to(dev))
-    assert _rel(o, gold["unet_out"]) < 1e-3  # fp32 (TF32 convs allowed by torch default, like the reference on GPU)
+    assert _rel(o, gold["unet_out"]) < 2e-5  # true fp32 on both sides (tests/conftest.py switches TF32 off)
 
 
 def test_full_unet_matches_reference_golden(udt_lib):
@@ -61,13 +61,13 @@ def test_full_unet_matches_reference_golden(udt_lib):
     torch.cuda.synchronize()
     err = _rel(y, gold["out"])
     print("full unet rel-L2 vs reference golden:", err, "max abs", (y.cpu() - gold["out"]).abs().max().item())
-    assert err < 1e-2
+    assert err < 2.7e-3  # 1.5 x the 1.77e-3 measured on B200 (profiles/parity_r02.json)
     for item, ref in zip(net.attn_map_cache, gold["probs_strided64"]):
         assert (item["attn_map"][:, ::64].cpu() - ref).abs().max().item() < 1e-2
-    # replay is reproducible (fp64 atomics in the GroupNorm statistics may flip a last bit)
+    # a second forward is bit-identical: no kernel of the path uses atomics or an order-dependent reduction
     y2 = net.forward(gold["x"], gold["t"], gold["ctx"])
     torch.cuda.synchronize()
-    assert (y - y2).abs().max().item() < 1e-4
+    assert torch.equal(y, y2)
 
 
 def test_uc_cross_attention_shortcut_is_exact(udt_lib):

@@ -37,7 +37,7 @@ def test_vae_encode_matches_oracle(udt_lib, name, hw):
     err = _rel(got, ref)
     print(f"vae encode {name} {hw}: rel-L2 {err:.3e}")
     assert tuple(got.shape) == tuple(ref.shape)
-    assert err < 1e-2
+    assert err < 2.2e-3      # fp16 storage through 11 ResnetBlocks: 1.5 x the 1.44e-3 measured on B200
 
 
 @pytest.mark.parametrize("name,lat", [("tiny", 8), ("tiny", 12), ("full", 32)])
@@ -57,4 +57,4 @@ def test_vae_decode_matches_oracle(udt_lib, name, lat):
     err = _rel(got, ref)
     print(f"vae decode {name} {lat}: rel-L2 {err:.3e} max-abs {(got - ref).abs().max().item():.3e}")
     assert tuple(got.shape) == tuple(ref.shape)
-    assert err < 1e-2
+    assert err < 8e-4        # 1.5 x the 5.3e-4 measured on B200 (decoded pixels in [0, 1])

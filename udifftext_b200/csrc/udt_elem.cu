@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(256) softmax_groups_kernel(const __half* __res
 // Character embedding + sinusoid positional encoding (encoders/modules.py:1160-1166, 1083-1085):
 // out fp16 [B*L, D] = emb[idx[b,l], :] + pe[l, :]
 __global__ void label_embed_kernel(const int32_t* __restrict__ idx, const float* __restrict__ emb,
-                                   const float* __restrict__ pe, __half* __restrict__ out, int rows, int L, int D) {
+                                   const float* __restrict__ pe, __half* __restrict__ out, float* __restrict__ out_f32,
+                                   __half* __restrict__ out_lo, int rows, int L, int D) {
   griddep_launch();   // PDL: let the next kernel's prologue start
   griddep_wait();     // PDL: wait for the producers of our inputs
   const size_t total = static_cast<size_t>(rows) * D;
@@ -226,7 +227,138 @@ __global__ void label_embed_kernel(const int32_t* __restrict__ idx, const float*
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int d = static_cast<int>(i % D);
     const int r = static_cast<int>(i / D);
-    out[i] = __float2half_rn(emb[static_cast<size_t>(idx[r]) * D + d] + pe[static_cast<size_t>(r % L) * D + d]);
+    const float v = emb[static_cast<size_t>(idx[r]) * D + d] + pe[static_cast<size_t>(r % L) * D + d];
+    const __half hi = __float2half_rn(v);
+    out[i] = hi;
+    if (out_f32 != nullptr) out_f32[i] = v;
+    if (out_lo != nullptr) out_lo[i] = __float2half_rn(v - __half2float(hi));
+  }
+}
+
+// ---- fp32-stream pieces of the LabelEncoder (its output conditions every step of every request, so its error is a
+// systematic one: it is evaluated with an fp32 residual stream and hi + lo fp16 operand pairs, see label.py)
+// y = LN( relu?( in0 + in1 + in2 ) + res ) per row (LN optional); y -> fp32 and / or the fp16 pair hi = rn(y), lo = rn(y - hi)
+constexpr int kRsThreads = 256;
+constexpr int kRsMaxPer = 32;   // C <= 256 * 32 = 8192
+
+__global__ void __launch_bounds__(kRsThreads) rowsum_norm_split_kernel(
+    const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ in2, const float* __restrict__ res,
+    int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu, float* __restrict__ out_f32,
+    __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  griddep_launch();
+  griddep_wait();
+  __shared__ float red[kRsThreads / 32];
+  __shared__ float bc;
+  const size_t base = static_cast<size_t>(blockIdx.x) * C;
+  float v[kRsMaxPer];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kRsMaxPer; ++i) {
+    const int c = threadIdx.x + i * kRsThreads;
+    float t = 0.0f;
+    if (c < C) {
+      t = in0[base + c];
+      if (in1 != nullptr) t += in1[base + c];
+      if (in2 != nullptr) t += in2[base + c];
+      if (relu) t = fmaxf(t, 0.0f);
+      if (res != nullptr) t += res[base + c];
+    }
+    v[i] = t;
+    s += t;
+  }
+  auto block_sum = [&](float x) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int w = 0; w < kRsThreads / 32; ++w) t += red[w];
+      bc = t;
+    }
+    __syncthreads();
+    return bc;
+  };
+  float mean = 0.0f, rstd = 1.0f;
+  if (gamma != nullptr) {
+    mean = block_sum(s) / static_cast<float>(C);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kRsMaxPer; ++i) {
+      const int c = threadIdx.x + i * kRsThreads;
+      if (c < C) {
+        const float d = v[i] - mean;
+        q += d * d;
+      }
+    }
+    rstd = rsqrtf(block_sum(q) / static_cast<float>(C) + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < kRsMaxPer; ++i) {
+    const int c = threadIdx.x + i * kRsThreads;
+    if (c < C) {
+      float y = v[i];
+      if (gamma != nullptr) y = (y - mean) * rstd * gamma[c] + beta[c];
+      if (out_f32 != nullptr) out_f32[base + c] = y;
+      if (out_hi != nullptr) {
+        const __half hi = __float2half_rn(y);
+        out_hi[base + c] = hi;
+        if (out_lo != nullptr) out_lo[base + c] = __float2half_rn(y - __half2float(hi));
+      }
+    }
+  }
+}
+
+// fp32 variant of mha_small: qkv fp32 [B*L, ld] (q | k | v), output as the fp16 pair hi / lo
+__global__ void __launch_bounds__(128) mha_small_f32_kernel(const float* __restrict__ qkv, __half* __restrict__ o_hi,
+                                                            __half* __restrict__ o_lo, int L, int heads, int dh, int ld, int ldo,
+                                                            float scale) {
+  griddep_launch();
+  griddep_wait();
+  extern __shared__ float smf[];
+  float* sq = smf;
+  float* sk = sq + L * dh;
+  float* sv = sk + L * dh;
+  float* sp = sv + L * dh;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int D = heads * dh;
+  for (int i = threadIdx.x; i < L * dh; i += blockDim.x) {
+    const int l = i / dh, d = i % dh;
+    const size_t off = (static_cast<size_t>(b) * L + l) * ld + h * dh + d;
+    sq[i] = qkv[off];
+    sk[i] = qkv[off + D];
+    sv[i] = qkv[off + 2 * D];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+    const int i = e / L, j = e % L;
+    float acc = 0.0f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(sq[i * dh + d], sk[j * dh + d], acc);
+    sp[e] = acc * scale;
+  }
+  __syncthreads();
+  if (threadIdx.x < L) {
+    float* row = sp + threadIdx.x * L;
+    float mx = -INFINITY;
+    for (int j = 0; j < L; ++j) mx = fmaxf(mx, row[j]);
+    float sum = 0.0f;
+    for (int j = 0; j < L; ++j) {
+      row[j] = expf(row[j] - mx);
+      sum += row[j];
+    }
+    const float inv = 1.0f / sum;
+    for (int j = 0; j < L; ++j) row[j] *= inv;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * dh; e += blockDim.x) {
+    const int i = e / dh, d = e % dh;
+    float acc = 0.0f;
+    for (int j = 0; j < L; ++j) acc = fmaf(sp[i * L + j], sv[j * dh + d], acc);
+    const size_t off = (static_cast<size_t>(b) * L + i) * ldo + h * dh + d;
+    const __half hi = __float2half_rn(acc);
+    o_hi[off] = hi;
+    o_lo[off] = __float2half_rn(acc - __half2float(hi));
   }
 }
 
@@ -394,13 +526,14 @@ __global__ void cfg_pack_kernel(const float* __restrict__ x, const float* __rest
 
 // x[B,4,HW] (NCHW) += dsigma * (eps_u + s*(eps_c - eps_u)); eps2b fp32 NHWC [2B,HW,4]
 __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps, int B, int HW, float s,
-                                 const float* __restrict__ dsigma_dev) {
+                                 const float* __restrict__ dsigma_dev, const float* __restrict__ scale_dev) {
   griddep_launch();   // PDL: let the next kernel's prologue start
   griddep_wait();     // PDL: wait for the producers of our inputs
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = B * HW;
   if (idx >= total) return;
   const float dsigma = __ldg(dsigma_dev);
+  if (scale_dev != nullptr) s = __ldg(scale_dev);   // per-request guidance scale from device memory (graph-stable)
   const int b = idx / HW, p = idx % HW;
   const float4 eu = *reinterpret_cast<const float4*>(eps + static_cast<size_t>(idx) * 4);
   const float4 ec = *reinterpret_cast<const float4*>(eps + (static_cast<size_t>(total) + idx) * 4);
@@ -685,15 +818,47 @@ extern "C" int udt_xattn_small_l(const void* q, const void* kc, const void* vc, 
   return check_launch("udt_xattn_small_l");
 }
 
-extern "C" int udt_label_embed(const int32_t* idx, const float* emb, const float* pe, void* out, int32_t rows,
-                               int32_t L, int32_t D, void* stream) {
+extern "C" int udt_label_embed(const int32_t* idx, const float* emb, const float* pe, void* out, float* out_f32, void* out_lo,
+                               int32_t rows, int32_t L, int32_t D, void* stream) {
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
   if (rows < 1 || L < 1 || D < 1) return fail(UDT_ERR_SHAPE, "udt_label_embed: rows=%d L=%d D=%d", rows, L, D);
   const size_t total = static_cast<size_t>(rows) * D;
-  udt_host::launch_pdl(label_embed_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-      idx, emb, pe, reinterpret_cast<__half*>(out), rows, L, D);
+  udt_host::launch_pdl(label_embed_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+      idx, emb, pe, reinterpret_cast<__half*>(out), out_f32, reinterpret_cast<__half*>(out_lo), rows, L, D);
   return check_launch("udt_label_embed");
+}
+
+extern "C" int udt_rowsum_norm_split(const float* in0, const float* in1, const float* in2, const float* res, int32_t rows,
+                                     int32_t C, const float* gamma, const float* beta, float eps, int32_t relu, float* out_f32,
+                                     void* out_hi, void* out_lo, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (rows < 1 || C < 1 || C > kRsThreads * kRsMaxPer || in0 == nullptr || (gamma != nullptr) != (beta != nullptr) ||
+      (out_lo != nullptr && out_hi == nullptr))
+    return fail(UDT_ERR_SHAPE, "udt_rowsum_norm_split: rows=%d C=%d (<= %d)", rows, C, kRsThreads * kRsMaxPer);
+  udt_host::launch_pdl(rowsum_norm_split_kernel, dim3(rows), dim3(kRsThreads), 0, reinterpret_cast<cudaStream_t>(stream), in0, in1,
+                       in2, res, C, gamma, beta, eps, relu, out_f32, reinterpret_cast<__half*>(out_hi),
+                       reinterpret_cast<__half*>(out_lo));
+  return check_launch("udt_rowsum_norm_split");
+}
+
+extern "C" int udt_mha_small_f32(const float* qkv, void* o_hi, void* o_lo, int32_t B, int32_t L, int32_t heads, int32_t dh,
+                                 int32_t ld, int32_t ldo, float scale, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (L < 1 || L > kMhaMaxL || dh < 1 || dh > kMhaMaxD || B < 1 || heads < 1 || ld < 3 * heads * dh || o_hi == nullptr ||
+      o_lo == nullptr)
+    return fail(UDT_ERR_SHAPE, "udt_mha_small_f32: L=%d (<=%d) dh=%d (<=%d) ld=%d", L, kMhaMaxL, dh, kMhaMaxD, ld);
+  const size_t smem = (static_cast<size_t>(3) * L * dh + static_cast<size_t>(L) * L) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mha_small_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  udt_host::launch_pdl(mha_small_f32_kernel, dim3(heads, B), dim3(128), smem, reinterpret_cast<cudaStream_t>(stream), qkv,
+                       reinterpret_cast<__half*>(o_hi), reinterpret_cast<__half*>(o_lo), L, heads, dh, ld, ldo, scale);
+  return check_launch("udt_mha_small_f32");
 }
 
 extern "C" int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int32_t heads, int32_t dh, int32_t ld,
@@ -758,13 +923,13 @@ extern "C" int udt_cfg_pack(const float* x, const float* concat_uc, const float*
 }
 
 extern "C" int udt_cfg_euler_step(float* x, const float* eps2b, int32_t B, int32_t HW, float cfg_scale,
-                                  const float* dsigma_dev, void* stream) {
+                                  const float* dsigma_dev, const float* cfg_scale_dev, void* stream) {
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
   if (B < 1 || HW < 1 || dsigma_dev == nullptr) return fail(UDT_ERR_SHAPE, "udt_cfg_euler_step: B=%d HW=%d", B, HW);
   const int total = B * HW;
   udt_host::launch_pdl(cfg_euler_kernel, dim3((total + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), x, eps2b, B, HW, cfg_scale,
-                                                                                          dsigma_dev);
+                                                                                          dsigma_dev, cfg_scale_dev);
   return check_launch("udt_cfg_euler_step");
 }
 

@@ -160,7 +160,7 @@ int make_tmap_nhwc_c32_strided(CUtensorMap* m, const void* ptr, uint64_t C, uint
 }  // namespace udt_host
 
 extern "C" {
-int udt_version(void) { return 4; }
+int udt_version(void) { return 5; }
 int udt_arch(void) { return udt_host::arch(); }
 const char* udt_last_error(void) { return udt_host::error_buffer(); }
 int udt_num_sms(void) { return udt_host::num_sms(); }

@@ -103,6 +103,8 @@ class DiffusionEngine:
     # ------------------------------------------------------------------------------------------ module surface
     def to(self, device):
         device = torch.device(device)
+        if device != self.device:
+            self._runners.clear()      # cached step graphs are bound to the old device's executor and buffers
         self.device = device
         self.model.to(device)
         self.first_stage_model.to(device)

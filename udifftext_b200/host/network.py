@@ -124,8 +124,9 @@ class UnifiedUNetModel(_Component):
             item["attn_map"] = None
 
     def save_attn_map(self, attn_type="t_attn", save_name="temp", tokens=""):
-        """openaimodel.py:559-591 without the seaborn figure (presentation is out of scope): mean over the selected
-        layers and heads of the last forward's maps, returned for the LAST sample as [tokens, h, w] (numpy)."""
+        """openaimodel.py:559-591: mean over the selected layers and heads of the last forward's exported maps; the
+        LAST sample's [tokens, h, w] map (numpy) is returned and drawn as the reference's 3 x 4 heat-map figure to
+        `temp/attn_map/attn_map_<save_name>.png` (PIL instead of seaborn, see host/attn_viz.py)."""
         maps, heads = [], 1
         for item in self._exec().attn_map_cache:
             name = item["name"]
@@ -138,7 +139,10 @@ class UnifiedUNetModel(_Component):
         bh, n, l = am.shape
         am = am.reshape(-1, heads, n, l).mean(1)
         side = int(n ** 0.5)
-        return am.permute(0, 2, 1).reshape(am.shape[0], l, side, side).numpy()[-1]
+        attn_map_i = am.permute(0, 2, 1).reshape(am.shape[0], l, side, side).numpy()[-1]
+        from .attn_viz import save_attn_figure
+        save_attn_figure(attn_map_i, tokens, f"temp/attn_map/attn_map_{save_name}.png")
+        return attn_map_i
 
     def forward(self, x, timesteps=None, t_context=None, v_context=None, y=None, **kwargs):
         assert y is None, "must specify y if and only if the model is class-conditional"

@@ -35,8 +35,8 @@ class StepRunner:
         self.kv = torch.zeros((nb * ctx_len, unet.kv_width), device=dev, dtype=torch.float16)
         self.unet_in = torch.zeros((nb, h, w, unet.cin_pad_store), device=dev, dtype=torch.float16)
         self.eps = torch.zeros((nb, h, w, unet.out_channels), device=dev, dtype=torch.float32)
-        # static per-step row: [emb_width rowbias | c_in | dsigma | pad]
-        self.row_width = (unet.emb_width + 2 + 3) // 4 * 4
+        # static per-step row: [emb_width rowbias | c_in | dsigma | cfg scale | pad]
+        self.row_width = (unet.emb_width + 3 + 3) // 4 * 4
         self.row = torch.zeros((1, self.row_width), device=dev, dtype=torch.float32)
         self.table: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -46,9 +46,14 @@ class StepRunner:
 
     # ------------------------------------------------------------------------------------------ per request
     def begin(self, x: torch.Tensor, cond: Dict, uc: Dict, denoiser: DiscreteDenoiser, sigmas: torch.Tensor,
-              s_churn: float = 0.0, s_tmin: float = 0.0, s_tmax: float = float("inf")) -> None:
-        """load the request state into the static buffers and precompute the whole schedule's step table"""
+              s_churn: float = 0.0, s_tmin: float = 0.0, s_tmax: float = float("inf"),
+              cfg_scale: Optional[float] = None) -> None:
+        """load the request state into the static buffers and precompute the whole schedule's step table; `cfg_scale`
+        is this request's guidance scale (read from the device row by the Euler kernel: the captured graph does not
+        depend on it)"""
         u = self.unet
+        if cfg_scale is not None:
+            self.cfg_scale = float(cfg_scale)
         self.x.copy_(x)
         self.cat_uc.copy_(uc["concat"])
         self.cat_c.copy_(cond["concat"])
@@ -69,6 +74,7 @@ class StepRunner:
         table[:, : u.emb_width] = u.temb_rowbias(k["idx"])
         table[:, u.emb_width] = k["c_in"].to(self.device)
         table[:, u.emb_width + 1] = (k["dsigma"] * k["eps_scale"]).to(self.device)
+        table[:, u.emb_width + 2] = self.cfg_scale
         self.table = table
         self.timesteps = k["idx"]
 
@@ -77,15 +83,15 @@ class StepRunner:
         u = self.unet
         ew = u.emb_width
         ops.cfg_pack(self.x, self.cat_uc, self.cat_c, self.row[0, ew: ew + 1], self.unet_in)
-        prev = u.export_attn_maps
+        prev = (u.export_attn_maps, u.skip_uc_xattn, u.xattn_fold)
         u.export_attn_maps = export
         u.skip_uc_xattn = self.skip_uc
         u.xattn_fold = self.fold if self.skip_uc else None
         try:
             u.forward_nhwc(self.unet_in, self.row[:, :ew].expand(2 * self.B, ew), self.kv, self.ctx_len, out=self.eps)
-        finally:
-            u.export_attn_maps = prev
-        ops.cfg_euler_step_(self.x, self.eps, self.cfg_scale, self.row[0, ew + 1: ew + 2])
+        finally:      # the shared UNetB200 must leave as it came: generic-path forwards run the full t_attn of both halves
+            u.export_attn_maps, u.skip_uc_xattn, u.xattn_fold = prev
+        ops.cfg_euler_step_(self.x, self.eps, self.cfg_scale, self.row[0, ew + 1: ew + 2], self.row[0, ew + 2: ew + 3])
 
     def _capture(self) -> None:
         self._body()                       # warm-up: lazy one-time initialisation must not happen under capture

@@ -64,6 +64,13 @@ class EDMSampler(SingleStepDiffusionSampler):
 
 
 class EulerEDMSampler(EDMSampler):
+    def save_segment_map(self, attn_maps, tokens=None, save_name=None):
+        """sampling.py:254-262: the first len(tokens) per-token maps -> ./temp/seg_map/seg_<name>.npy (demo.py:105)"""
+        import os
+        section = np.stack([attn_maps[i] for i in range(len(tokens))])
+        os.makedirs("./temp/seg_map", exist_ok=True)
+        np.save(f"./temp/seg_map/seg_{save_name}.npy", section)
+
     # ------------------------------------------------------------------------------------------ fused path
     def _fused_ok(self, model) -> bool:
         net = getattr(model.model, "diffusion_model", None)
@@ -72,14 +79,21 @@ class EulerEDMSampler(EDMSampler):
                 and isinstance(model.model, OpenAIWrapper) and isinstance(net, UnifiedUNetModel)
                 and type(self.guider.dyn_thresh).__name__ == "NoDynamicThresholding" and self.s_churn == 0.0)
 
+    MAX_RUNNERS = 4    # cached step graphs per engine (each owns the UNet step's activations): least recently used goes
+
     def _runner(self, model, x, cond) -> StepRunner:
+        """the StepRunner (static buffers + captured step graph) for this request shape.  The guidance scale is NOT part
+        of the key — the Euler kernel reads it from the per-step device row — and the cache is a small LRU, so a demo
+        whose sliders change scale / num_samples / resolution per request does not accumulate graphs."""
         b, _, h, w = x.shape
         ctx_len = cond["t_crossattn"].shape[1]
-        key = (b, h, w, ctx_len, float(self.guider.scale))
-        r = model._runners.get(key)
+        key = (b, h, w, ctx_len)
+        r = model._runners.pop(key, None)
         if r is None:
             r = StepRunner(model.model.diffusion_model._exec(), b, h, w, ctx_len, self.guider.scale)
-            model._runners[key] = r
+            while len(model._runners) >= self.MAX_RUNNERS:
+                model._runners.pop(next(iter(model._runners)))
+        model._runners[key] = r          # (re)inserted last = most recently used
         return r
 
     # ------------------------------------------------------------------------------------------ noise search
@@ -95,18 +109,27 @@ class EulerEDMSampler(EDMSampler):
         if iters == 0:
             return randn
         verbose, self.verbose = self.verbose, False
+        fused = self._fused_ok(model)
         best_noise, best_loss = randn.clone(), torch.full((shape[0],), float("inf"), device=dev)
         worst = torch.full((shape[0],), -float("inf"), device=dev)
         trial_losses = []
         for _ in range(iters):
             x = randn.clone()
             x, _, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps=2)
-            runner = self._runner(model, x, cond)
-            runner.begin(x, cond, uc, model.denoiser, sigmas)
-            for i in range(num_sigmas - 1):
-                runner.step(i, export_attn_maps=True)
-            loss = model.loss_fn.get_min_local_loss(model.model.diffusion_model.attn_map_cache, batch["mask"], batch["seg_mask"])
-            loss = loss[loss.shape[0] // 2:]                      # conditional half of the CFG batch (:341)
+            if fused:
+                runner = self._runner(model, x, cond)
+                runner.begin(x, cond, uc, model.denoiser, sigmas, self.s_churn, self.s_tmin, self.s_tmax,
+                             cfg_scale=self.guider.scale)
+                for i in range(num_sigmas - 1):
+                    runner.step(i, export_attn_maps=True)
+                loss = model.loss_fn.get_min_local_loss(model.model.diffusion_model.attn_map_cache, batch["mask"],
+                                                        batch["seg_mask"])
+                loss = loss[loss.shape[0] // 2:]                  # conditional half of the CFG batch (:341)
+            else:                                                 # any other guider / denoiser / churn: the reference's loop
+                s_in = x.new_ones([x.shape[0]])
+                for i in range(num_sigmas - 1):
+                    x, _, loss = self.sampler_step(s_in * sigmas[i], s_in * sigmas[i + 1], model, x, cond, batch, uc,
+                                                   self._gamma(sigmas[i], num_sigmas), save_loss=True)
             trial_losses.append(loss)
             better = loss < best_loss
             best_noise[better] = randn[better]
@@ -141,7 +164,8 @@ class EulerEDMSampler(EDMSampler):
         else:
             loss = torch.zeros(1)
         if save_attn:
-            net.save_attn_map(save_name=name, tokens=batch["label"][0])
+            attn_map = net.save_attn_map(save_name=name, tokens=batch["label"][0])
+            self.save_segment_map(attn_map, tokens=batch["label"][0], save_name=name)
         d = to_d(x, sigma_hat, denoised)
         return self.euler_step(x, d, append_dims(next_sigma - sigma_hat, x.ndim)), inter, loss
 
@@ -152,15 +176,23 @@ class EulerEDMSampler(EDMSampler):
         if aae_enabled:
             raise NotImplementedError("aae_enabled (attend-and-excite) needs autograd through the UNet; out of scope")
         x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
+        if batch is not None and "name" in batch:
+            name = batch["name"][0]                   # sampling.py:362
         if not self._fused_ok(model):
             for i in self.get_sigma_gen(num_sigmas, init_step):
                 gamma = self._gamma(sigmas[i], num_sigmas)
                 x, _, _ = self.sampler_step(s_in * sigmas[i], s_in * sigmas[i + 1], model, x, cond, batch, uc, gamma,
-                                            save_attn=detailed and (i == (num_sigmas - 1) // 2))
+                                            name=name, save_attn=detailed and (i == (num_sigmas - 1) // 2))
             return x
         runner = self._runner(model, x, cond)
-        runner.begin(x, cond, uc, model.denoiser, sigmas, self.s_churn, self.s_tmin, self.s_tmax)
+        runner.begin(x, cond, uc, model.denoiser, sigmas, self.s_churn, self.s_tmin, self.s_tmax,
+                     cfg_scale=self.guider.scale)
+        net = model.model.diffusion_model
         for i in self.get_sigma_gen(num_sigmas, init_step):
-            runner.step(i, export_attn_maps=detailed and (i == (num_sigmas - 1) // 2))
+            save_attn = detailed and (i == (num_sigmas - 1) // 2)
+            runner.step(i, export_attn_maps=save_attn)
+            if save_attn:                             # sampling.py:344-346: the files demo.py:104-105 reads back
+                attn_map = net.save_attn_map(save_name=name, tokens=batch["label"][0])
+                self.save_segment_map(attn_map, tokens=batch["label"][0], save_name=name)
         self.last_runner = runner
         return runner.result()

@@ -146,6 +146,52 @@ def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
     return {"by_op": acc, "step_ms_eager_sum": total, "step_ms_graph": step_ms_graph, "by_shape": shapes}
 
 
+def profile_step_in_graph(runner, replays: int = 12) -> dict:
+    """Per-entry-point device time of one sampler step measured INSIDE a captured graph of the whole step: the step is
+    captured once more with an external timing event (an event-record graph node) after every C-ABI call; the graph is
+    replayed `replays` times back to back (clocks settle at what a long request sees) and the node-to-node intervals of
+    the last replay are summed per entry point.  An interval spans from the completion of the previous call to the
+    completion of this one, so it contains the launch gap the event node puts between two kernels (programmatic dependent
+    launch cannot overlap across it): the sums are upper bounds of the kernels' time in the product's step graph, whose
+    duration is returned beside them (`step_ms_graph_with_events` vs the plain graph)."""
+    x_saved = runner.x.clone()
+    runner.row.copy_(runner.table[0:1])
+    runner._body()
+    torch.cuda.synchronize()
+    marks = []          # (entry point, event recorded after the call)
+
+    g = torch.cuda.CUDAGraph()
+    orig_invoke = globals()["_invoke"]
+
+    def traced(name, *args, shape=None):
+        orig_invoke(name, *args, shape=shape)
+        e = torch.cuda.Event(enable_timing=True, external=True)
+        e.record()
+        marks.append((name, e))
+
+    with torch.cuda.graph(g):
+        start = torch.cuda.Event(enable_timing=True, external=True)
+        start.record()
+        globals()["_invoke"] = traced
+        try:
+            runner._body()
+        finally:
+            globals()["_invoke"] = orig_invoke
+    for _ in range(replays):
+        g.replay()
+    torch.cuda.synchronize()
+    acc: dict = {}
+    prev = start
+    for name, e in marks:
+        a = acc.setdefault(name, {"ms": 0.0, "calls": 0})
+        a["ms"] += prev.elapsed_time(e)
+        a["calls"] += 1
+        prev = e
+    total = start.elapsed_time(marks[-1][1])
+    runner.x.copy_(x_saved)
+    return {"by_op": acc, "step_ms_graph_with_events": total}
+
+
 _SPLITK_WS = {}   # device index -> fp32 scratch for split-K partial tiles (stream ordered, shared by all calls)
 SPLITK_WS_BYTES = 64 << 20
 
@@ -399,13 +445,41 @@ def attn_local_score(probs: torch.Tensor, mask: torch.Tensor, seg: torch.Tensor,
             b, bm, heads, size, probs.shape[2], seg.shape[1], hh, ww, gk.shape[-1])
 
 
-def label_embed(idx: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor) -> torch.Tensor:
-    """idx int32 [B, L]; emb fp32 [V, D]; pe fp32 [L, D] -> fp16 [B*L, D]"""
+def label_embed(idx: torch.Tensor, emb: torch.Tensor, pe: torch.Tensor, out: Optional[torch.Tensor] = None,
+                out_f32: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """idx int32 [B, L]; emb fp32 [V, D]; pe fp32 [L, D] -> fp16 [B*L, D] (optionally also fp32 and the low fp16 half)"""
     b, l = idx.shape
     d = emb.shape[1]
-    out = torch.empty((b * l, d), device=emb.device, dtype=torch.float16)
-    _invoke("udt_label_embed", idx.data_ptr(), emb.data_ptr(), pe.data_ptr(), out.data_ptr(), b * l, l, d)
+    if out is None:
+        out = torch.empty((b * l, d), device=emb.device, dtype=torch.float16)
+    _invoke("udt_label_embed", idx.data_ptr(), emb.data_ptr(), pe.data_ptr(), out.data_ptr(), _ptr(out_f32), _ptr(out_lo),
+            b * l, l, d)
     return out
+
+
+def rowsum_norm_split(parts: Sequence[torch.Tensor], res: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+                      beta: Optional[torch.Tensor] = None, eps: float = 1e-5, relu: bool = False,
+                      out_f32: Optional[torch.Tensor] = None, out_hi: Optional[torch.Tensor] = None,
+                      out_lo: Optional[torch.Tensor] = None) -> None:
+    """y = LN(relu?(sum(parts)) + res) row-wise over fp32 [rows, C] tensors (1-3 parts; LN optional) -> fp32 and / or the
+    fp16 pair hi / lo (udt_rowsum_norm_split)"""
+    rows, c = parts[0].shape
+    for t in list(parts) + [t for t in (res, out_f32) if t is not None]:
+        assert t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (rows, c)
+    for t in (out_hi, out_lo):
+        assert t is None or (t.dtype == torch.float16 and t.is_contiguous() and tuple(t.shape) == (rows, c))
+    p = [t.data_ptr() for t in parts] + [None] * (3 - len(parts))
+    _invoke("udt_rowsum_norm_split", p[0], p[1], p[2], _ptr(res), rows, c, _ptr(gamma), _ptr(beta), float(eps), int(relu),
+            _ptr(out_f32), _ptr(out_hi), _ptr(out_lo))
+
+
+def mha_small_f32(qkv: torch.Tensor, b: int, l: int, heads: int, out_hi: torch.Tensor, out_lo: torch.Tensor) -> None:
+    """qkv fp32 [B*L, 3*D] (q | k | v) -> the fp16 pair out_hi / out_lo [B*L, D]; softmax scale = head_dim^-0.5"""
+    d = qkv.shape[1] // 3
+    dh = d // heads
+    assert qkv.dtype == torch.float32 and qkv.is_contiguous()
+    _invoke("udt_mha_small_f32", qkv.data_ptr(), out_hi.data_ptr(), out_lo.data_ptr(), b, l, heads, dh, qkv.stride(0),
+            out_hi.stride(0), float(dh) ** -0.5)
 
 
 def mha_small(qkv: torch.Tensor, b: int, l: int, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -435,11 +509,14 @@ def cfg_pack(x: torch.Tensor, cat_uc: torch.Tensor, cat_c: torch.Tensor, c_in_de
     return out
 
 
-def cfg_euler_step_(x: torch.Tensor, eps2b: torch.Tensor, cfg_scale: float, dsigma_dev: torch.Tensor) -> torch.Tensor:
-    """x fp32 NCHW [B,4,h,w] += dsigma * cfg(eps2b fp32 NHWC [2B,h,w,4]); dsigma_dev: device fp32 scalar"""
+def cfg_euler_step_(x: torch.Tensor, eps2b: torch.Tensor, cfg_scale: float, dsigma_dev: torch.Tensor,
+                    cfg_scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 NCHW [B,4,h,w] += dsigma * cfg(eps2b fp32 NHWC [2B,h,w,4]); dsigma_dev: device fp32 scalar; `cfg_scale_dev`
+    (device fp32 scalar) overrides `cfg_scale` when given"""
     b = x.shape[0]
     hw = x.numel() // (b * 4)
-    _invoke("udt_cfg_euler_step", x.data_ptr(), eps2b.data_ptr(), b, hw, float(cfg_scale), dsigma_dev.data_ptr())
+    _invoke("udt_cfg_euler_step", x.data_ptr(), eps2b.data_ptr(), b, hw, float(cfg_scale), dsigma_dev.data_ptr(),
+            _ptr(cfg_scale_dev))
     return x
 
 

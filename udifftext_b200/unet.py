@@ -171,8 +171,7 @@ class UNetB200:
         self.emb_width = self.w_emb.shape[0]
         half = model_channels // 2
         self._freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half).to(dev)
-        self._gn_ws: Optional[torch.Tensor] = None
-        self._gn_ws_nb = 0
+        self._gn_ws: Dict[int, torch.Tensor] = {}     # one workspace per batch size, never reallocated (graph-stable)
         self._max_hw = 128 * 128
         self.st_layers: List[_ST] = [l[1] for blk in self.input_plan + [self.middle_plan] + self.output_plan
                                      for l in blk if l[0] == "st"]
@@ -191,13 +190,16 @@ class UNetB200:
 
     # ------------------------------------------------------------------------------------------ pieces
     def _ws(self, nb: int) -> torch.Tensor:
-        """GroupNorm partial-statistics workspace (shared by all calls: they are stream ordered)."""
-        if self._gn_ws is None or self._gn_ws_nb < nb:
+        """GroupNorm partial-statistics workspace (shared by all calls of one batch size: they are stream ordered).
+        Captured step graphs hold its raw pointer, so a workspace is never freed or replaced while the model lives:
+        a larger batch gets its own buffer instead of growing (and thereby freeing) the one a cached graph writes to."""
+        ws = self._gn_ws.get(nb)
+        if ws is None:
             hw = self._max_hw
             need = max(ops.groupnorm_ws_bytes(nb, hw, c) for c in (64, 320, 640, 960, 1280, 1920, 2560, 4096)) // 8
-            self._gn_ws = torch.empty(need, device=self.device, dtype=torch.float64)
-            self._gn_ws_nb = nb
-        return self._gn_ws
+            ws = torch.empty(need, device=self.device, dtype=torch.float64)
+            self._gn_ws[nb] = ws
+        return ws
 
     def temb_rowbias(self, timesteps: torch.Tensor) -> torch.Tensor:
         """[NB] integer timesteps -> fp32 [NB, emb_width]: all emb_layers outputs (without conv bias).
