@@ -31,6 +31,7 @@ extern "C" {
 #define UDT_ACT_SILU 1
 #define UDT_ACT_GEGLU 2 /* out[:, j] = x_j * gelu_erf(gate_j); weight rows interleaved per column tile */
 #define UDT_ACT_RELU 3
+#define UDT_ACT_GELU 4 /* exact (erf) GELU: PARSeq's ViT MLP and decoder FFN (strhub/models/parseq/modules.py:33-50) */
 
 int udt_version(void);            /* ABI version (5: udt_cfg_euler_step takes cfg_scale_dev; fp32-stream LabelEncoder entry points) */
 int udt_arch(void);               /* compute capability of the current device *10 (100 on B200); <0 on error */
@@ -168,6 +169,16 @@ int udt_mha_small_f32(const float* qkv, void* o_hi, void* o_lo, int32_t B, int32
 int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int32_t heads, int32_t dh, int32_t ld, int32_t ldo,
                   float scale, void* stream);
 
+/* Multi-head attention over short sequences with masks — the self- / cross-attention of PARSeq's two-stream decoder layer
+ * (src/parseq/strhub/models/parseq/modules.py:57-75, nn.MultiheadAttention batch_first; OCR scoring of test.py:58-91):
+ * o[b, i, h*dh:(h+1)*dh] = softmax_j( q_i . k_j * scale + mask[i, j] ; -inf where key_padding_mask[b, j] ) v_j.
+ * q fp16 [B*Lq, ldq], k / v fp16 [B*Lk, ldk / ldv] (head h at columns [h*dh, h*dh + dh)), o fp16 [B*Lq, ldo];
+ * mask fp32 [Lq, ldm] additive (may hold -inf) or NULL; key_padding_mask uint8 [B, Lk] (non-zero = ignore) or NULL;
+ * Lk <= 160, dh <= 64.  A fully masked row yields zeros. */
+int udt_mha_masked(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t Lq, int32_t Lk, int32_t heads,
+                   int32_t dh, int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale, const float* mask, int32_t ldm,
+                   const uint8_t* key_padding_mask, void* stream);
+
 /* Folded textual cross-attention (attention.py:140-174 with the step-invariant K / V of the 12 context tokens folded into
  * the projections; exact in real arithmetic):
  *   scores[m, h*L + l] = LN(t)[m, :] . W1[s(m)][h*L + l, :],   W1[s][h*L + l, c] = scale * sum_d K[s, l, h*64 + d] * Wq[h*64 + d, c]
@@ -216,10 +227,6 @@ int udt_pointwise_affine(const float* x, const float* Wm, const float* bias, voi
 /* data movement helpers */
 /* nearest-neighbour 2x upsample of NHWC fp16 (openaimodel.py:99; model.py:65) */
 int udt_upsample2x_nhwc(const void* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream);
-/* explicit im2col for the rare convs the TMA path does not cover (C_in not a multiple of 64, stride 2,
- * asymmetric VAE padding model.py:77-85): out fp16 [NB*Ho*Wo, Kpad], K order (tap, channel), zero padded. */
-int udt_im2col3x3_nhwc(const void* x, void* out, int32_t NB, int32_t H, int32_t W, int32_t C, int32_t ld,
-                       int32_t stride, int32_t pad_lo, int32_t Ho, int32_t Wo, int32_t Kpad, void* stream);
 /* layout / dtype conversion at the API boundary: NCHW fp32 <-> NHWC fp16 (channel padded with zeros) */
 int udt_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t NB, int32_t C, int32_t HW, int32_t Cpad, void* stream);
 int udt_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* y, int32_t NB, int32_t C, int32_t HW, int32_t ld,

@@ -10,7 +10,7 @@ inference (`embedder.train = disabled_train` is installed before `model.eval()`,
 util.py:18-20), so dropout(p=0.1) makes the text embedding random.  Golden vectors are generated with the
 LabelEncoder switched to eval mode (`nn.Module.train(le, False)`) — the deterministic function both sides share.
 
-usage: python oracle/make_golden.py [tiny] [loss] [noise_search] [full_unet] [c1]
+usage: python oracle/make_golden.py [tiny] [loss] [noise_search] [full_unet] [c1] [parseq]
 """
 import os
 import sys
@@ -214,8 +214,57 @@ def gen_noise_search():
                 "min_attn_size": lf.min_attn_size}, os.path.join(GOLD, "noise_search.pt"))
 
 
+def gen_parseq():
+    """PARSeq (OCR scoring): the unmodified reference PARSeq (AR decode + 1 refinement) on seeded weights and
+    seeded 32x128 inputs -> logits + decoded strings; oracle/parseq_restated.py must reproduce both.  Also pins
+    ParseqPredictor's crop preprocessing (torchvision Resize BICUBIC antialias + Normalize) against torchvision itself."""
+    from oracle import parseq_restated as PR
+    PARSeq = ref_import.import_reference_parseq()
+    import yaml
+    cfgd = os.path.join(ref_import.REFERENCE_ROOT, "src", "parseq", "configs")
+    cfg = yaml.safe_load(open(os.path.join(cfgd, "main.yaml")))["model"]
+    cfg.update(yaml.safe_load(open(os.path.join(cfgd, "charset", "94_full.yaml")))["model"])
+    cfg.update(yaml.safe_load(open(os.path.join(cfgd, "model", "parseq.yaml"))))
+    for k in ("_convert_", "_target_", "name"):
+        cfg.pop(k, None)
+    cfg["lr"] = float(cfg["lr"])
+    model = PARSeq(**cfg).eval()
+    sd = synth.synthetic_state_dict(synth.parseq_manifest(), 4321)
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(99)
+    images = torch.randn((3, 3, 32, 128), generator=g)
+    with torch.no_grad():
+        ref_logits = model(images)
+        ref_txt, _ = model.tokenizer.decode(ref_logits.softmax(-1))
+        got = PR.forward(sd, images)
+        memory = model.encode(images)
+    got_txt, _ = PR.Tokenizer(cfg["charset_train"]).decode(got.softmax(-1))
+    print("parseq logits", tuple(ref_logits.shape), "restated rel", rel(got, ref_logits), ref_txt, got_txt)
+    assert got.shape == ref_logits.shape and rel(got, ref_logits) < 1e-5 and got_txt == ref_txt
+    assert cfg["charset_train"] == PR.CHARSET_94
+    tok_ref = model.tokenizer.encode(["Hello", "B200!"])
+    assert torch.equal(tok_ref, PR.Tokenizer().encode(["Hello", "B200!"]))
+    # crop preprocessing of ParseqPredictor.forward vs torchvision
+    from torchvision import transforms
+    tf = transforms.Compose([transforms.Resize((32, 128), transforms.InterpolationMode.BICUBIC, antialias=True),
+                             transforms.Normalize(0.5, 0.5)])
+    crops = [torch.rand((3, 57, 203), generator=g), torch.rand((3, 128, 384), generator=g)]
+    ref_pre = torch.cat([tf(t[None]) for t in crops])
+    assert rel(PR.preprocess(crops), ref_pre) < 1e-6
+    with torch.no_grad():            # one image whose AR loop stops early (EOS at step 3): the refinement still queries 26 positions
+        ref_single = model(images[2:3])
+        got_single = PR.forward(sd, images[2:3])
+    print("parseq early stop", tuple(ref_single.shape), rel(got_single, ref_single))
+    assert got_single.shape == ref_single.shape and rel(got_single, ref_single) < 1e-5
+    torch.save({"seed": 4321, "images": images.half(), "logits": ref_logits, "text": ref_txt, "memory_f16": memory.half(),
+                "logits_single": ref_single,
+                "crops_seed": 99, "pre": ref_pre.half()}, os.path.join(GOLD, "parseq.pt"))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["tiny"]
+    if "parseq" in what:
+        gen_parseq()
     os.makedirs(GOLD, exist_ok=True)
     if "tiny" in what:
         gen_tiny()

@@ -63,10 +63,19 @@ def install_shims() -> None:
     import transformers  # noqa: F401  (must be imported before the stand-ins shadow its optional deps)
 
     class LightningModule(nn.Module):
+        _device = torch.device("cpu")      # pytorch_lightning's device mixin (strhub/models/parseq/system.py reads it)
+
+        @property
+        def device(self):
+            return self._device
+
         def log(self, *a, **k):
             pass
 
         def log_dict(self, *a, **k):
+            pass
+
+        def save_hyperparameters(self, *a, **k):
             pass
 
     _mod("pytorch_lightning", LightningModule=LightningModule, seed_everything=lambda s: torch.manual_seed(s),
@@ -93,6 +102,32 @@ def install_shims() -> None:
     _mod("timm")
     _mod("timm.models")
     _mod("timm.models.vision_transformer", VisionTransformer=nn.Module)
+
+
+def import_reference_parseq():
+    """the reference's bundled PARSeq (src/parseq/strhub) with the ABSENT third-party `timm` replaced by the restated ViT
+    of oracle/parseq_restated.py (timm's published algorithm); everything else — PARSeq.forward / decode, Decoder,
+    DecoderLayer, TokenEmbedding, Tokenizer — is the unmodified reference code.  Returns the PARSeq class."""
+    install_shims()
+    from oracle import parseq_restated as PR
+    sys.modules["pytorch_lightning"].utilities = _mod("pytorch_lightning.utilities")
+    _mod("pytorch_lightning.utilities.types", STEP_OUTPUT=object)
+
+    def named_apply(fn, module, name="", depth_first=True, include_root=False):
+        for child_name, child in module.named_children():
+            named_apply(fn, child, ".".join((name, child_name)) if name else child_name, depth_first, True)
+        if include_root:
+            fn(module=module, name=name)
+        return module
+
+    _mod("timm.models.vision_transformer", VisionTransformer=PR.RestatedViT, PatchEmbed=PR.PatchEmbed)
+    _mod("timm.models.helpers", named_apply=named_apply)
+    _mod("timm.optim", create_optimizer_v2=lambda *a, **k: None)
+    root = os.path.join(REFERENCE_ROOT, "src", "parseq")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from strhub.models.parseq.system import PARSeq
+    return PARSeq
 
 
 def import_reference():

@@ -13,7 +13,7 @@ from udifftext_b200 import ops, pack  # noqa: E402
 def main():
     which = sys.argv[1:] or ["linear", "conv", "fmha", "ln", "gn", "xattn", "conv8"]
     dev = torch.device("cuda", 0)
-    nb = 8
+    nb = int(os.environ.get("UDT_NCU_NB", "8"))     # UNet batch (2 x images): 8 = configs[1], 64 = configs[2]
     reps = int(os.environ.get("UDT_NCU_REPS", "3"))
     if "linear" in which:
         m, k, n = nb * 4096, 320, 320

@@ -25,37 +25,6 @@ import torch
 import torch.nn.functional as F
 
 
-def quantised_oracle(R, mode: str):
-    """context manager: oracle GEMMs / convs with operands rounded to fp16 (emulates fp16 storage, fp32 accumulation)
-    mode: 'w' weights only; 'wa' weights + GEMM/conv inputs; 'was' + every GEMM/conv output (all stored activations)"""
-    import contextlib
-
-    q = lambda t: t.half().float()
-
-    @contextlib.contextmanager
-    def cm():
-        lin, conv = R._lin, R._conv
-
-        def _lin(sd, name, x):
-            w = q(sd[name + ".weight"])
-            xi = q(x) if "a" in mode else x
-            y = F.linear(xi, w, sd.get(name + ".bias"))
-            return q(y) if "s" in mode else y
-
-        def _conv(sd, name, x, stride=1, padding=1):
-            w = q(sd[name + ".weight"])
-            xi = q(x) if "a" in mode else x
-            y = F.conv2d(xi, w, sd.get(name + ".bias"), stride=stride, padding=padding)
-            return q(y) if "s" in mode else y
-
-        R._lin, R._conv = _lin, _conv
-        try:
-            yield
-        finally:
-            R._lin, R._conv = lin, conv
-    return cm()
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity.json"))
@@ -102,7 +71,7 @@ def main():
     if args.study:
         study = {}
         for mode in ("w", "wa", "was"):
-            with quantised_oracle(R, mode):
+            with P.quantised_oracle(R, mode):
                 oq = P.oracle_run(R, sd_dev, batch_dev, steps, 5.0, 1002)
             study[mode] = {"pixels_rel": P.rel(oq["pixels"], ora["pixels"]), "latents_rel": P.rel(oq["z"], ora["z"]),
                            "eps_rel_step0": P.rel(oq["eps"][0], ora["eps"][0]),
@@ -130,7 +99,7 @@ def main():
         st2 = {}
         for phase in ("cond", "unet", "dec"):
             for mode in ("w", "was"):
-                oq = P.oracle_run(R, sd_dev, batch_dev, steps, 5.0, 1002, phase_ctx={phase: (lambda m=mode: quantised_oracle(R, m))})
+                oq = P.oracle_run(R, sd_dev, batch_dev, steps, 5.0, 1002, phase_ctx={phase: (lambda m=mode: P.quantised_oracle(R, m))})
                 st2[f"{phase}_{mode}"] = {"pixels_rel": P.rel(oq["pixels"], ora["pixels"]), "latents_rel": P.rel(oq["z"], ora["z"]),
                                           "c_concat_rel": P.rel(oq["c"]["concat"], ora["c"]["concat"]),
                                           "t_crossattn_rel": P.rel(oq["c"]["t_crossattn"], ora["c"]["t_crossattn"])}

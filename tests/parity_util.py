@@ -11,6 +11,38 @@ import contextlib
 from typing import Dict, List, Optional, Sequence
 
 import torch
+import torch.nn.functional as F
+
+
+def quantised_oracle(R, mode: str):
+    """context manager: oracle GEMMs / convs with operands rounded to fp16 (emulates fp16 storage, fp32 accumulation)
+    mode: 'w' weights only; 'wa' weights + GEMM/conv inputs; 'was' + every GEMM/conv output (all stored activations)"""
+    import contextlib
+
+    q = lambda t: t.half().float()
+
+    @contextlib.contextmanager
+    def cm():
+        lin, conv = R._lin, R._conv
+
+        def _lin(sd, name, x):
+            w = q(sd[name + ".weight"])
+            xi = q(x) if "a" in mode else x
+            y = F.linear(xi, w, sd.get(name + ".bias"))
+            return q(y) if "s" in mode else y
+
+        def _conv(sd, name, x, stride=1, padding=1):
+            w = q(sd[name + ".weight"])
+            xi = q(x) if "a" in mode else x
+            y = F.conv2d(xi, w, sd.get(name + ".bias"), stride=stride, padding=padding)
+            return q(y) if "s" in mode else y
+
+        R._lin, R._conv = _lin, _conv
+        try:
+            yield
+        finally:
+            R._lin, R._conv = lin, conv
+    return cm()
 
 
 @contextlib.contextmanager

@@ -277,3 +277,18 @@ def test_request_batch_u8_validates_its_inputs():
         api.request_batch_u8(cfgs, img, np.zeros((32, 64, 3), dtype=np.uint8), "abc", 2)   # mask of another size
     with pytest.raises(ValueError):
         api.request_batch_u8(cfgs, img, img, "x" * 13, 2)                            # longer than seq_len
+
+
+@pytest.mark.skipif(not has_ref, reason="reference checkout not mounted (GPU box)")
+def test_reference_test_py_and_demo_py_run_on_the_dropin():
+    """the UNMODIFIED /root/reference/test.py (predict + test() with the shipped configs/test.yaml, ocr_enabled: True ->
+    sgm.modules.predictors.model.ParseqPredictor) and demo.py (demo_predict) execute against the drop-in `sgm` package with
+    a stubbed device layer: model / sampler are autospec images of our real classes, so every call the reference makes is
+    checked against our signatures (tests/_ref_entrypoints_check.py)"""
+    import subprocess
+    import tempfile
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ref_entrypoints_check.py")], capture_output=True,
+                         text=True, cwd=tempfile.gettempdir())
+    assert out.returncode == 0, out.stderr[-3000:]
+    for what in ("OK test.py predict", "OK test.py test() with configs/test.yaml (ocr_enabled)", "OK demo.py demo_predict"):
+        assert what in out.stdout, out.stdout[-2000:]

@@ -122,32 +122,6 @@ def test_conv3x3_fused_skip_and_residual(udt_lib):
     assert _rel(y2.float().cpu().permute(0, 3, 1, 2), ref2) < 2e-3
 
 
-@pytest.mark.parametrize("stride,pad_lo,cin", [(1, 1, 9), (2, 1, 64), (2, 0, 32)])
-def test_im2col_conv_paths(udt_lib, stride, pad_lo, cin):
-    """first conv (Cin=9), UNet stride-2 (pad 1) and VAE stride-2 (pad (0,1,0,1)) through im2col + GEMM."""
-    from udifftext_b200 import ops, pack
-    dev = _dev()
-    g = torch.Generator().manual_seed(stride * 10 + cin)
-    nb, h, w, cout = 2, 32, 32, 128
-    x = _randn((nb, cin, h, w), g).half()
-    wt = _randn((cout, cin, 3, 3), g, 1 / math.sqrt(9 * cin)).half()
-    if pad_lo == 0:
-        ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wt.float(), None, stride=2)
-    else:
-        ref = F.conv2d(x.float(), wt.float(), None, stride=stride, padding=1)
-    ho, wo = ref.shape[2], ref.shape[3]
-    cpad = (cin + 7) // 8 * 8
-    xh = torch.zeros((nb, h, w, cpad), dtype=torch.float16)
-    xh[..., :cin] = x.permute(0, 2, 3, 1)
-    kpad = (9 * cpad + 63) // 64 * 64
-    wpad = torch.zeros((cout, cpad, 3, 3))
-    wpad[:, :cin] = wt.float()
-    cols = ops.im2col3x3(xh.to(dev), stride, pad_lo, ho, wo, kpad)
-    y = ops.linear(cols, pack.pack_conv3x3_padded(wpad, kpad).to(dev))
-    torch.cuda.synchronize()
-    assert _rel(y.float().cpu().reshape(nb, ho, wo, cout).permute(0, 3, 1, 2), ref) < 2e-3
-
-
 @pytest.mark.parametrize("stride,pad,cin,cstore,h,w", [(1, 1, 9, 16, 32, 32), (2, 1, 64, 64, 32, 32), (2, 0, 32, 32, 32, 32),
                                                       (2, 1, 320, 320, 64, 64), (2, 0, 128, 128, 64, 48), (1, 1, 3, 8, 40, 24),
                                                       (2, 1, 640, 640, 16, 16), (2, 0, 512, 512, 8, 8)])
@@ -324,37 +298,31 @@ def test_vae_sample_pack_and_pointwise_affine(udt_lib):
     n_c, n_uc = _randn((b, 4, h, w), g), _randn((b, 4, h, w), g)
     mask = (torch.rand((b, 1, 8 * h, 8 * w), generator=g) > 0.5).float()
     mom_nhwc = moments.permute(0, 2, 3, 1).contiguous()
-    # fp64 reference (an fp32 CPU evaluation was seen to disagree by up to 2e-4 once, in the first process of a cold box;
-    # 400 back-to-back launches are bit-identical and within 2.4e-7 of the reference — scripts/k10_stress.py)
+    # fp64 reference with a bound derived from the arithmetic: the kernel evaluates scale * fma(sd, noise, mean) in fp32, so
+    # |got - exact| <= a few ulp of the TERMS (|mean| + sd |noise|), not of the possibly cancelling result; sd reaches e^10.
+    # (Root cause of the "rare cold-box mismatch" this test once retried: its first version compared against an fp32 CPU
+    # evaluation, whose exp / mul-add rounding depends on the host CPU's vector path; with sd ~ 2e4 one ulp of sd * noise is
+    # 4e-3, i.e. up to 2e-4 of the old metric.  The kernel itself is deterministic — launches are bit-identical below and
+    # over 400 fresh uploads in scripts/k10_stress.py — so there is nothing to retry.)
     m8 = F.interpolate(mask.double(), scale_factor=0.125, mode="bilinear")
+    sd64 = torch.exp(0.5 * torch.clamp(moments[:, 4:].double(), -30.0, 20.0))
     refs = (torch.cat([m8, 0.18215 * R.posterior_sample(moments.double(), n_c.double())], dim=1),
             torch.cat([m8, 0.18215 * R.posterior_sample(moments.double(), n_uc.double())], dim=1))
-
-    def attempt():
-        d_in = (mom_nhwc.to(dev), n_c.to(dev), n_uc.to(dev), mask.to(dev))
-        first = ops.vae_sample_pack(*d_in, 0.18215)
-        again = ops.vae_sample_pack(*d_in, 0.18215)              # elementwise kernel: launches must be bit-identical
-        torch.cuda.synchronize()
-        assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1]), "K10 is not deterministic"
-        problems = []
-        for got, ref, nz in zip(first, refs, (n_c, n_uc)):
-            err = (got.cpu().double() - ref).abs() / (1.0 + ref.abs())
-            if err.max().item() >= 1e-5:
-                i = int(err.argmax())
-                bi, ci, yi, xi = [int(v) for v in torch.unravel_index(torch.tensor(i), err.shape)]
-                problems.append(
-                    f"worst element {(bi, ci, yi, xi)}: got {got.cpu().flatten()[i].item()!r} ref {ref.flatten()[i].item()!r}; "
-                    f"elements above tol: {(err >= 1e-5).sum().item()}; inputs mean/logvar/noise "
-                    f"{moments[bi, max(ci - 1, 0), yi, xi].item()!r} {moments[bi, 4 + max(ci - 1, 0), yi, xi].item()!r} "
-                    f"{nz[bi, max(ci - 1, 0), yi, xi].item()!r}")
-        return problems
-
-    problems = attempt()
-    if problems:       # one re-run with fresh uploads tells a persistent error from the rare cold-box mismatch
-        import warnings
-        warnings.warn("K10 first attempt off tolerance: " + " | ".join(problems))
-        problems = attempt()
-    assert not problems, problems
+    d_in = (mom_nhwc.to(dev), n_c.to(dev), n_uc.to(dev), mask.to(dev))
+    first = ops.vae_sample_pack(*d_in, 0.18215)
+    again = ops.vae_sample_pack(*d_in, 0.18215)              # elementwise kernel: launches must be bit-identical
+    torch.cuda.synchronize()
+    assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1]), "K10 is not deterministic"
+    for got, ref, nz in zip(first, refs, (n_c, n_uc)):
+        terms = torch.cat([torch.ones_like(m8), 0.18215 * (moments[:, :4].double().abs() + sd64 * nz.double().abs())], dim=1)
+        err = (got.cpu().double() - ref).abs()
+        bound = 1e-6 * terms + 1e-7
+        if not bool((err <= bound).all()):
+            i = int((err / bound).argmax())
+            bi, ci, yi, xi = [int(v) for v in torch.unravel_index(torch.tensor(i), err.shape)]
+            raise AssertionError(
+                f"K10 worst element {(bi, ci, yi, xi)}: got {got.cpu().flatten()[i].item()!r} ref {ref.flatten()[i].item()!r} "
+                f"bound {bound.flatten()[i].item():.3e}; elements above the bound: {(err > bound).sum().item()}")
     z = _randn((b, 4, h, w), g)
     wm = _randn((4, 4), g)
     bias = _randn((4,), g)

@@ -103,3 +103,23 @@ def test_oracle_noise_search_matches_reference_golden(tiny_sd):
     assert torch.allclose(losses, gold["losses"], atol=1e-5)
     assert torch.equal(best, gold["best"])
     assert (gold["losses"].max() - gold["losses"].min()).item() > 1e-3      # the trials are distinguishable
+
+
+def test_parseq_restatement_matches_reference_golden():
+    """oracle/parseq_restated.py vs the unmodified reference PARSeq run in the build container (tests/golden/parseq.pt:
+    logits of 3 seeded images incl. one whose AR loop stops early, decoded strings, crop preprocessing vs torchvision)"""
+    from oracle import parseq_restated as PR
+    from udifftext_b200 import synth
+    gold = torch.load(os.path.join(GOLD, "parseq.pt"))
+    sd = synth.synthetic_state_dict(synth.parseq_manifest(), gold["seed"])
+    images = gold["images"].float()
+    with torch.no_grad():
+        got = PR.forward(sd, images)
+        single = PR.forward(sd, images[2:3])
+    assert got.shape == gold["logits"].shape and _rel(got, gold["logits"]) < 2e-4      # inputs stored as fp16
+    assert PR.Tokenizer().decode(got.softmax(-1))[0] == gold["text"]
+    assert single.shape == gold["logits_single"].shape and _rel(single, gold["logits_single"]) < 2e-4
+    g = torch.Generator().manual_seed(gold["crops_seed"])
+    torch.randn((3, 3, 32, 128), generator=g)                                          # the images draw of make_golden
+    crops = [torch.rand((3, 57, 203), generator=g), torch.rand((3, 128, 384), generator=g)]
+    assert _rel(PR.preprocess(crops), gold["pre"].float()) < 1e-3

@@ -34,9 +34,11 @@ def _nvcc() -> str:
 
 
 def _flags() -> list:
-    """UDT_TRACE=1 compiles the role-timeline trace and the UDT_IGEMM_DEBUG experiment switches into udt_igemm
-    (scripts/igemm_trace.py); production builds leave them out of the hot loops."""
-    return NVCC_FLAGS + (["-DUDT_IGEMM_TRACE"] if os.environ.get("UDT_TRACE", "0") not in ("", "0") else [])
+    """UDT_TRACE=1 gives a TUNING build: the role-timeline trace of udt_igemm (scripts/igemm_trace.py) and every experiment
+    switch (UDT_* environment variables, udt_host.h tune_int) are compiled in.  A production build contains neither: it
+    reads no environment variable and keeps debug code out of the hot loops."""
+    tuning = os.environ.get("UDT_TRACE", "0") not in ("", "0")
+    return NVCC_FLAGS + (["-DUDT_IGEMM_TRACE", "-DUDT_TUNING"] if tuning else [])
 
 
 def _source_digest() -> str:

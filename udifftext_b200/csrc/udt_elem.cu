@@ -1,5 +1,5 @@
 // udt_elem.cu — HBM-bound glue kernels of the hot path: K5 short-context cross-attention, row softmax,
-// K7 CFG pack / Euler step, nearest 2x upsample, im2col for the rare convs outside the TMA path, and the
+// K7 CFG pack / Euler step, nearest 2x upsample, the LabelEncoder / PARSeq small-sequence attentions and the
 // NCHW fp32 <-> NHWC fp16 conversions at the API boundary.  All 16-byte vectorised where the layout allows.
 #include "udt_common.cuh"
 #include "udt_host.h"
@@ -415,6 +415,72 @@ __global__ void __launch_bounds__(kMhaThreads) mha_small_kernel(const __half* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------- masked small MHA
+// nn.MultiheadAttention over short sequences with an additive attention mask and a boolean key-padding mask: the self- and
+// cross-attention of PARSeq's two-stream decoder layer (src/parseq/strhub/models/parseq/modules.py:57-75; OCR scoring,
+// test.py:58-91).  One CTA per (head, batch item): this head's K / V rows staged in shared memory as fp32 (row pitch dh + 1:
+// conflict-free when the lanes walk the keys), one warp per query row: lanes stride over the keys for the scores, warp
+// softmax, lanes stride over the head dim for P V.  A fully masked row yields zeros.
+constexpr int kMmThreads = 128;
+constexpr int kMmMaxLk = 160;
+constexpr int kMmMaxDh = 64;
+
+__global__ void __launch_bounds__(kMmThreads) mha_masked_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                                const __half* __restrict__ v, __half* __restrict__ o, int Lq, int Lk,
+                                                                int dh, int ldq, int ldk, int ldv, int ldo, float scale,
+                                                                const float* __restrict__ mask, int ldm,
+                                                                const uint8_t* __restrict__ kpm) {
+  griddep_launch();
+  griddep_wait();
+  extern __shared__ float smm[];
+  const int pitch = dh + 1;
+  float* sk = smm;
+  float* sv = sk + Lk * pitch;
+  float* sq = sv + Lk * pitch;                 // [warps][dh]
+  float* sp = sq + (kMmThreads / 32) * dh;     // [warps][Lk]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < Lk * dh; i += blockDim.x) {
+    const int j = i / dh, d = i - j * dh;
+    sk[j * pitch + d] = __half2float(k[(static_cast<size_t>(b) * Lk + j) * ldk + h * dh + d]);
+    sv[j * pitch + d] = __half2float(v[(static_cast<size_t>(b) * Lk + j) * ldv + h * dh + d]);
+  }
+  __syncthreads();
+  float* myq = sq + warp * dh;
+  float* myp = sp + warp * Lk;
+  for (int i = warp; i < Lq; i += kMmThreads / 32) {
+    const size_t qrow = static_cast<size_t>(b) * Lq + i;
+    for (int d = lane; d < dh; d += 32) myq[d] = __half2float(q[qrow * ldq + h * dh + d]);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) {
+      float acc = 0.0f;
+      for (int d = 0; d < dh; ++d) acc = fmaf(myq[d], sk[j * pitch + d], acc);
+      acc *= scale;
+      if (mask != nullptr) acc += mask[static_cast<size_t>(i) * ldm + j];
+      if (kpm != nullptr && kpm[static_cast<size_t>(b) * Lk + j]) acc = -INFINITY;
+      myp[j] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float e = (mx == -INFINITY) ? 0.0f : __expf(myp[j] - mx);
+      myp[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float acc = 0.0f;
+      for (int j = 0; j < Lk; ++j) acc = fmaf(myp[j], sv[j * pitch + d], acc);
+      o[qrow * ldo + h * dh + d] = __float2half_rn(acc * inv);
+    }
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- row softmax
 // One CTA per row; cols up to 16384 (VAE attention N = 4096 / 9216), values cached in registers.
 constexpr int kSmThreads = 256;
@@ -622,30 +688,6 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
   }
 }
 
-// out[(n,oy,ox), tap*C + c] = x[n, oy*stride - pad_lo + ky, ox*stride - pad_lo + kx, c]; columns >= 9*C zero.
-__global__ void im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ out, int NB, int H, int W, int C,
-                                 int ld, int stride, int pad_lo, int Ho, int Wo, int Kpad) {
-  griddep_launch();   // PDL: let the next kernel's prologue start
-  griddep_wait();     // PDL: wait for the producers of our inputs
-  const size_t total = static_cast<size_t>(NB) * Ho * Wo * Kpad;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % Kpad);
-    size_t r = i / Kpad;
-    const int ox = static_cast<int>(r % Wo);
-    r /= Wo;
-    const int oy = static_cast<int>(r % Ho);
-    const int n = static_cast<int>(r / Ho);
-    __half v = __float2half(0.0f);
-    if (k < 9 * C) {
-      const int tap = k / C, c = k % C;
-      const int iy = oy * stride - pad_lo + tap / 3;
-      const int ix = ox * stride - pad_lo + tap % 3;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<size_t>(n) * H + iy) * W + ix) * ld + c];
-    }
-    out[i] = v;
-  }
-}
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restrict__ y, int NB, int C, int HW, int Cpad) {
   griddep_launch();   // PDL: let the next kernel's prologue start
@@ -873,6 +915,25 @@ extern "C" int udt_mha_small(const void* qkv, void* o, int32_t B, int32_t L, int
   return check_launch("udt_mha_small");
 }
 
+extern "C" int udt_mha_masked(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t Lq, int32_t Lk,
+                              int32_t heads, int32_t dh, int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale,
+                              const float* mask, int32_t ldm, const uint8_t* key_padding_mask, void* stream) {
+  int rc = require_sm100();
+  if (rc != UDT_OK) return rc;
+  if (B < 1 || Lq < 1 || Lk < 1 || Lk > kMmMaxLk || heads < 1 || dh < 1 || dh > kMmMaxDh || (mask != nullptr && ldm < Lk))
+    return fail(UDT_ERR_SHAPE, "udt_mha_masked: Lq=%d Lk=%d (<=%d) dh=%d (<=%d)", Lq, Lk, kMmMaxLk, dh, kMmMaxDh);
+  const size_t smem = (static_cast<size_t>(2) * Lk * (dh + 1) + (kMmThreads / 32) * (dh + Lk)) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mha_masked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  udt_host::launch_pdl(mha_masked_kernel, dim3(heads, B), dim3(kMmThreads), smem, reinterpret_cast<cudaStream_t>(stream),
+                       reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(k), reinterpret_cast<const __half*>(v),
+                       reinterpret_cast<__half*>(o), Lq, Lk, dh, ldq, ldk, ldv, ldo, scale, mask, ldm, key_padding_mask);
+  return check_launch("udt_mha_masked");
+}
+
 extern "C" int udt_softmax_rows(void* x, int32_t rows, int32_t cols, int32_t ld, float scale, void* stream) {
   int rc = require_sm100();
   if (rc != UDT_OK) return rc;
@@ -965,17 +1026,6 @@ extern "C" int udt_upsample2x_nhwc(const void* x, void* y, int32_t NB, int32_t H
   udt_host::launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), NB, H, W, C / 8);
   return check_launch("udt_upsample2x_nhwc");
-}
-
-extern "C" int udt_im2col3x3_nhwc(const void* x, void* out, int32_t NB, int32_t H, int32_t W, int32_t C, int32_t ld,
-                                  int32_t stride, int32_t pad_lo, int32_t Ho, int32_t Wo, int32_t Kpad, void* stream) {
-  int rc = require_sm100();
-  if (rc != UDT_OK) return rc;
-  if (Kpad < 9 * C || Kpad % 8) return fail(UDT_ERR_SHAPE, "udt_im2col3x3_nhwc: Kpad=%d < 9*C=%d", Kpad, 9 * C);
-  const size_t total = static_cast<size_t>(NB) * Ho * Wo * Kpad;
-  udt_host::launch_pdl(im2col3x3_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), NB, H, W, C, ld, stride, pad_lo, Ho, Wo, Kpad);
-  return check_launch("udt_im2col3x3_nhwc");
 }
 
 extern "C" int udt_nchw_f32_to_nhwc_f16(const float* x, void* y, int32_t NB, int32_t C, int32_t HW, int32_t Cpad,

@@ -1,9 +1,9 @@
 // udt_fmha.cu — K4: softmax(Q K^T * scale) V for head dim 64 on tcgen05 tensor cores (sm_100a).
 //
 // One CTA owns two 128-row query tiles of one (batch, head) and streams the keys/values in 128-row tiles:
-//   warp 9      TMA producer : Q tiles once, then a 3-stage ring of K / V tiles (128B-swizzled boxes)
+//   warp 9      TMA producer : Q tiles once, then a 4-stage ring of K / V tiles (128B-swizzled boxes)
 //   warp 8      MMA issuer   : S = Q_t K_j^T     (M128 N128 K64, K-major operands)       -> one of THREE S buffers in TMEM
-//                              O_t += P_t V_j    (M128 N64 K128, V as MN-major operand)  -> TMEM O_t (accumulating)
+//                              O_t += P_t V_j    (M128 N64 K128, P from TMEM, V MN-major) -> TMEM O_t (accumulating)
 //                              The score tiles of both query tiles rotate through three TMEM buffers, so the scores a
 //                              softmax warpgroup needs next are computed while it still works on its current tile
 //                              (with one buffer per query tile the exp pipe idled during every S MMA).
@@ -13,17 +13,17 @@
 //                              over the reference maximum — the probabilities are then bounded by 256, safe in
 //                              fp16, and the final division by the row sum uses the same reference.  After the first
 //                              key tile the scores are read from TMEM ONCE: exponentials are taken against the current
-//                              reference while the tile maximum is tracked, and only a (rare) violation of the 2^8
+//                              reference while the row sum is tracked, and only a (rare) violation of the 2^8
 //                              bound replays the tile.  The tcgen05.ld of the next 32 columns flies during the math.
 //                              P_t goes back into TENSOR MEMORY as fp16 pairs over the first 64 columns of its own
 //                              (fully consumed) score buffer and feeds the PV MMA as a TMEM A operand (TS form):
-//                              tcgen05.st is 4x faster than tcgen05.ld, no shared-memory round trip, and the freed
-//                              64 KB of P buffers buy a 4-stage K / V ring (udt_fmha_ts_kernel, +4-5 % over the
-//                              smem-P kernel udt_fmha_kernel, which is kept for A/B runs: UDT_FMHA_TS=0).
+//                              tcgen05.st is 4x faster than tcgen05.ld, no shared-memory round trip, and the shared
+//                              memory a P buffer would need buys the 4-stage K / V ring.
+// Floors per 128x128 score tile (measured): tcgen05.ld 64 B/clk/SM -> 1024 clk; MUFU.EX2 16/clk/SM -> 1024 clk
+// (`ex2.approx.f16x2` is NOT a way around it: ptxas emits two MUFU.EX2.F16 + a PRMT for it on sm_100a); the MMAs need 512 clk.
 // Replaces xformers.ops.memory_efficient_attention at reference sgm/modules/attention.py:246-248.
 #include "udt_common.cuh"
 #include "udt_host.h"
-#include <stdlib.h>
 
 namespace {
 
@@ -32,8 +32,7 @@ using namespace udt;
 constexpr int kTile = 128;
 constexpr int kD = 64;
 constexpr int kTileBytes = kTile * kD * 2;  // 16 KB: Q tile, K tile, V tile
-constexpr int kPBytes = kTile * kTile * 2;  // 32 KB per query tile
-constexpr int kKvStages = 3;
+constexpr int kKvStages = 4;   // K / V ring depth
 constexpr int kSBufs = 3;
 constexpr int kThreads = 320;
 constexpr int kTmemCols = 512;
@@ -89,15 +88,10 @@ __device__ __forceinline__ bool fmha_work(const FmhaParams& p, int& b, int& h, i
   return q0 < p.Nq;
 }
 
-// smem layout (offsets from the 1024-aligned base)
+// smem layout (offsets from the 1024-aligned base): control words, 2 Q tiles, the K ring, the V ring (P lives in TMEM)
 constexpr int kOffCtrl = 0;
 constexpr int kOffQ = 1024;
-constexpr int kOffK = kOffQ + 2 * kTileBytes;
-constexpr int kOffV = kOffK + kKvStages * kTileBytes;
-constexpr int kOffP = kOffV + kKvStages * kTileBytes;
-constexpr int kSmemBytes = kOffP + 2 * kPBytes + 1024;
-// TS variant (P kept in TMEM): no P buffers, a deeper K / V ring instead
-constexpr int kTsKvStages = 4;
+constexpr int kTsKvStages = kKvStages;
 constexpr int kTsOffK = kOffQ + 2 * kTileBytes;
 constexpr int kTsOffV = kTsOffK + kTsKvStages * kTileBytes;
 constexpr int kTsSmemBytes = kTsOffV + kTsKvStages * kTileBytes + 1024;
@@ -116,294 +110,6 @@ struct CompCursor {
     }
   }
 };
-
-__global__ void __launch_bounds__(kThreads, 1) udt_fmha_kernel(const __grid_constant__ FmhaParams p) {
-  griddep_launch();   // PDL: let the next kernel's prologue start
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
-  uint8_t* base = smem_raw + (base_addr - raw_addr);
-
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(base + kOffCtrl);
-  uint64_t* kv_full = q_full + 1;            // [kKvStages]
-  uint64_t* kv_empty = kv_full + kKvStages;  // [kKvStages]
-  uint64_t* s_full = kv_empty + kKvStages;   // [kSBufs]  scores of a computation are in TMEM
-  uint64_t* s_free = s_full + kSBufs;        // [kSBufs]  the consuming warpgroup has read them
-  uint64_t* p_full = s_free + kSBufs;        // [2]       P_t(j) is in shared memory
-  uint64_t* o_full = p_full + 2;             // [2]       P_t(j) V_j has been accumulated into O_t
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  int b, h, q0, ntiles;
-  if (!fmha_work(p, b, h, q0, ntiles)) return;           // odd tile count: the second half of the last pair is empty
-  const int nkv = (p.Nkv + kTile - 1) / kTile;
-  const int ncomp = nkv * ntiles;
-
-  if (warp == 9 && lane == 0) {
-    tma_prefetch_desc(&p.mapQ);
-    tma_prefetch_desc(&p.mapK);
-    tma_prefetch_desc(&p.mapV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kKvStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    for (int i = 0; i < kSBufs; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 128);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&p_full[i], 128);
-      mbar_init(&o_full[i], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 8) tmem_alloc<kTmemCols>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  griddep_wait();     // PDL: q / k / v are produced by the previous kernel
-
-  if (warp == 9) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const int col = h * kD;
-      mbar_expect_tx(q_full, static_cast<uint32_t>(ntiles * kTileBytes));
-      for (int t = 0; t < ntiles; ++t)
-        tma_load_2d(&p.mapQ, q_full, base + kOffQ + t * kTileBytes, col, b * p.Nq + q0 + t * kTile);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1u);
-        mbar_expect_tx(&kv_full[s], 2u * kTileBytes);
-        tma_load_2d(&p.mapK, &kv_full[s], base + kOffK + s * kTileBytes, col, b * p.Nkv + j * kTile);
-        tma_load_2d(&p.mapV, &kv_full[s], base + kOffV + s * kTileBytes, col, b * p.Nkv + j * kTile);
-        if (++s == kKvStages) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
-    const bool issuer = elect_one();
-    const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
-    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
-    auto issue_s = [&](const CompCursor& k) {
-      if (k.t == 0) mbar_wait(&kv_full[k.stage], static_cast<uint32_t>(k.kvphase));
-      if (k.u > 0) mbar_wait(&s_free[k.b], static_cast<uint32_t>((k.u - 1) & 1));   // the previous user has read this buffer
-      tc_fence_after();
-      if (issuer) {
-        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + k.t * kTileBytes);
-        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kOffK + k.stage * kTileBytes);
-#pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk)
-          umma_f16_ss(tmem_base + kColS + k.b * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
-                      idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&s_full[k.b]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    CompCursor ks, kp;   // score cursor runs kSBufs computations ahead of the PV cursor
-    ks.init();
-    kp.init();
-    for (int i = 0; i < kSBufs && ks.c < ncomp; ++i) {
-      issue_s(ks);
-      ks.advance(ntiles);
-    }
-    for (; kp.c < ncomp; kp.advance(ntiles)) {
-      mbar_wait(&p_full[kp.t], static_cast<uint32_t>(kp.j & 1));   // P_t(j) is in smem, S of this computation is released
-      tc_fence_after();
-      if (issuer) {
-        const uint32_t v_addr = base_addr + kOffV + kp.stage * kTileBytes;
-        const uint32_t p_addr = base_addr + kOffP + kp.t * kPBytes;
-        if (!UDT_FDBG(4))
-#pragma unroll
-        for (int kk = 0; kk < kTile / 16; ++kk) {
-          const uint64_t dp = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32);
-          const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
-          umma_f16_ss(tmem_base + kColO + kp.t * 64, dp, dv, idesc_o, (kp.j | kk) != 0 ? 1u : 0u);
-        }
-        umma_commit(&o_full[kp.t]);
-        if (kp.t == ntiles - 1) umma_commit(&kv_empty[kp.stage]);   // last reader of this K/V stage
-      }
-      __syncwarp();
-      if (ks.c < ncomp) {
-        issue_s(ks);
-        ks.advance(ntiles);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    const int t = warp >> 2;  // query tile handled by this warpgroup
-    if (t < ntiles) {
-      const int quarter = warp & 3;
-      const int row = quarter * 32 + lane;
-      const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t o_addr = tmem_base + lane_base + kColO + t * 64;
-      uint8_t* sP = base + kOffP + t * kPBytes;
-      const float sl2 = p.scale_log2;
-      float m_ref = -INFINITY, l = 0.0f;
-      int sb = t, su = 0;   // S buffer / use count of this warpgroup's next computation (c = j * ntiles + t)
-
-      // rescale the running output (and row sum) when the reference maximum moves; O_t must be stable
-      auto rescale = [&](bool need, float m_tile, int j) {
-        const float m_new = need ? m_tile : m_ref;
-        const float alpha = need ? ex2_approx(m_ref - m_new) : 1.0f;  // m_ref = -inf on the first tile -> 0
-        l *= alpha;
-        if (j > 0) {
-          mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(o_addr + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(o_addr + c * 32, v);
-          }
-          tmem_st_wait();
-        }
-        m_ref = m_new;
-      };
-
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&s_full[sb], static_cast<uint32_t>(su & 1));
-        tc_fence_after();
-        const uint32_t s_addr = tmem_base + lane_base + kColS + sb * 128;
-        const int key_lim = p.Nkv - j * kTile;  // keys >= key_lim of this tile are padding (only on the last tile)
-        const bool partial = key_lim < kTile;
-        float rowsum = 0.0f;
-        bool replay = (j == 0) || partial;      // first / ragged tile: maximum first, then the exponentials
-        if (j > 0) {
-          mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));  // P_t V_{j-1} done: the P buffer is reusable, O_t stable
-          tc_fence_after();
-        }
-        // 32 probabilities (keys [32*ch, 32*ch+32) of this tile) -> fp16 -> this row's swizzled slots of the P buffer;
-        // the stores interleave with the exponentials of the following chunk
-        auto store_chunk = [&](const uint32_t (&pk)[16], int ch) {
-          uint8_t* prow = sP + (ch >> 1) * kTileBytes + row * 128;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c16 = (ch & 1) * 4 + g;   // 16-byte group within the 128-byte row of this 64-key half
-            *reinterpret_cast<uint4*>(prow + ((c16 ^ (row & 7)) << 4)) =
-                make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-          }
-        };
-        if (!replay) {
-          // ---- single pass: exponentials against the current reference, written to the P buffer right away.  No
-          // maximum is tracked: every probability is bounded by 2^8 unless the tile's row sum exceeds 2^8, so a row sum
-          // above that bound (rare: the reference would have to be stale by almost the whole lazy margin) sends the tile
-          // through the two-pass path, which overwrites the optimistic P (nobody reads it before p_full).
-          uint32_t va[32], vb[32];
-          auto exp_chunk = [&](const uint32_t (&vv)[32], int ch) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float p0 = fmaf(__uint_as_float(vv[i]), sl2, -m_ref);
-              float p1 = fmaf(__uint_as_float(vv[i + 1]), sl2, -m_ref);
-              if (!UDT_FDBG(1)) {
-                p0 = ex2_approx(p0);
-                p1 = ex2_approx(p1);
-              }
-              rowsum += p0 + p1;
-              pk[i >> 1] = pack_half2(p0, p1);
-            }
-            if (!UDT_FDBG(2)) store_chunk(pk, ch);
-          };
-          tmem_ld32(s_addr, va);
-          tmem_ld_wait_dep(va);
-          tmem_ld32(s_addr + 32, vb);      // the next 32 columns fly during the math
-          exp_chunk(va, 0);
-          tmem_ld_wait_dep(vb);
-          tmem_ld32(s_addr + 64, va);
-          exp_chunk(vb, 1);
-          tmem_ld_wait_dep(va);
-          tmem_ld32(s_addr + 96, vb);
-          exp_chunk(va, 2);
-          tmem_ld_wait_dep(vb);
-          exp_chunk(vb, 3);
-          replay = __any_sync(0xffffffffu, !(rowsum <= 256.0f)) && !UDT_FDBG(3);   // also catches inf / nan
-        }
-        if (replay) {
-          // ---- two passes: row maximum of the raw scores, reference update (+ O rescale), exponentials
-          uint32_t v[32];
-          float mx = -INFINITY;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            tmem_ld32(s_addr + ch * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (!partial || ch * 32 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
-          const float m_tile = mx * sl2;
-          const bool need = m_tile > m_ref + kLazyThreshold;
-          if (__any_sync(0xffffffffu, need)) rescale(need, m_tile, j);
-          rowsum = 0.0f;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            tmem_ld32(s_addr + ch * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
-              float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
-              if (partial) {
-                const int k0 = ch * 32 + i;
-                if (k0 >= key_lim) p0 = 0.0f;
-                if (k0 + 1 >= key_lim) p1 = 0.0f;
-              }
-              rowsum += p0 + p1;
-              pk[i >> 1] = pack_half2(p0, p1);
-            }
-            store_chunk(pk, ch);
-          }
-        }
-        // the scores are consumed: hand the buffer back to the MMA warp
-        tc_fence_before();
-        mbar_arrive(&s_free[sb]);
-        l += rowsum;
-        fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
-        tc_fence_before();         // TMEM reads of S / writes of O_t ordered before the arrive
-        mbar_arrive(&p_full[t]);
-        sb += ntiles;
-        if (sb >= kSBufs) { sb -= kSBufs; ++su; }
-      }
-      mbar_wait(&o_full[t], static_cast<uint32_t>((nkv - 1) & 1));
-      tc_fence_after();
-      const int qrow = q0 + t * kTile + row;
-      const float inv = 1.0f / l;
-      uint4* o4 = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.Nq + min(qrow, p.Nq - 1)) * p.ldo + h * kD);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(o_addr + c * 32, v);
-        tmem_ld_wait();
-        if (qrow < p.Nq) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 ov;
-            ov.x = pack_half2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
-            ov.y = pack_half2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
-            ov.z = pack_half2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
-            ov.w = pack_half2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
-            o4[c * 4 + g] = ov;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) {
-    tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
-  }
-}
 
 // kPoly > 0: every kPoly-th exponential of the single-pass path is evaluated by ex2_poly instead of MUFU.EX2
 template <int kPoly>
@@ -703,12 +409,6 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   if (rc != UDT_OK) return rc;
   if (B < 1 || Nq < 1 || Nkv < 1 || heads < 1) return fail(UDT_ERR_SHAPE, "udt_fmha_fwd: bad shape");
   if (ldo % 8 || (reinterpret_cast<uintptr_t>(o) & 15)) return fail(UDT_ERR_ALIGN, "udt_fmha_fwd: o / ldo alignment");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(udt_fmha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha smem): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   FmhaParams p;
   rc = make_tmap_2d(&p.mapQ, q, static_cast<uint64_t>(heads) * kD, static_cast<uint64_t>(B) * Nq, ldq, kD, kTile);
   if (rc != UDT_OK) return rc;
@@ -722,33 +422,27 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   p.heads = heads;
   p.ldo = ldo;
   p.scale_log2 = scale * 1.4426950408889634f;
-  static const int dbg = [] { const char* e = getenv("UDT_FMHA_DEBUG"); return e ? atoi(e) : 0; }();
+  static const int dbg = tune_int("UDT_FMHA_DEBUG", 0);
   p.debug = dbg;
   p.pairs_per_bh = (Nq + 2 * kTile - 1) / (2 * kTile);
   const long npairs = static_cast<long>(p.pairs_per_bh) * heads * B;
   if (npairs > (1l << 30)) return fail(UDT_ERR_SHAPE, "udt_fmha_fwd: too many query tiles");
-  // tail wave: if its R pairs occupy at most half of the SMs, run them as 2R single-tile CTAs (UDT_FMHA_TAIL=0: never)
-  static const int tail_split = [] { const char* e = getenv("UDT_FMHA_TAIL"); return e ? atoi(e) : 1; }();
+  // tail wave: if its R pairs occupy at most half of the SMs, run them as 2R single-tile CTAs (tuning builds: UDT_FMHA_TAIL=0)
+  static const int tail_split = tune_int("UDT_FMHA_TAIL", 1);
   const int nsm = num_sms();
   const int tail = static_cast<int>(npairs % nsm);
   p.pairs_full = static_cast<int32_t>((tail_split && tail > 0 && 2 * tail <= nsm) ? npairs - tail : npairs);
   dim3 grid(static_cast<unsigned>(p.pairs_full + 2 * (npairs - p.pairs_full)), 1, 1);
-  // P kept in TMEM (TS-form PV MMA) is the production schedule; UDT_FMHA_TS=0 selects the smem-P kernel for A/B measurements
-  static const int use_ts = [] { const char* e = getenv("UDT_FMHA_TS"); return e ? atoi(e) : 1; }();
-  if (use_ts) {
-    // experiment switch: UDT_FMHA_POLY=4 moves every 4th exponential from MUFU to the FMA pipe.  Measured on B200: no gain
-    // (4096 tokens 249.0 -> 250.4 us; every 2nd: 275 us) — the kernel is bound by the TMEM read path, not by MUFU
-    static const int poly = [] { const char* e = getenv("UDT_FMHA_POLY"); return e ? atoi(e) : 0; }();
-    void (*kern)(FmhaParams) = poly == 0 ? udt_fmha_ts_kernel<0> : udt_fmha_ts_kernel<4>;
-    static bool ts_attr = false;
-    if (!ts_attr) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
-      if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha ts smem): %s", cudaGetErrorString(e));
-      ts_attr = true;
-    }
-    udt_host::launch_pdl(kern, dim3(grid), dim3(kThreads), kTsSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
-    return check_launch("udt_fmha_fwd (ts)");
+  // tuning builds: UDT_FMHA_POLY=4 moves every 4th exponential from MUFU to the FMA pipe.  Measured on B200: no gain
+  // (4096 tokens 249.0 -> 250.4 us; every 2nd: 275 us) — the kernel is bound by the TMEM read path as much as by MUFU
+  static const int poly = tune_int("UDT_FMHA_POLY", 0);
+  void (*kern)(FmhaParams) = poly == 0 ? udt_fmha_ts_kernel<0> : udt_fmha_ts_kernel<4>;
+  static bool ts_attr = false;
+  if (!ts_attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
+    if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha smem): %s", cudaGetErrorString(e));
+    ts_attr = true;
   }
-  udt_host::launch_pdl(udt_fmha_kernel, dim3(grid), dim3(kThreads), kSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
+  udt_host::launch_pdl(kern, dim3(grid), dim3(kThreads), kTsSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("udt_fmha_fwd");
 }

@@ -72,11 +72,7 @@ int arch() {
 }
 
 int pdl_attr(cudaLaunchAttribute* attr) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("UDT_PDL");
-    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-  }
+  static const int enabled = tune_int("UDT_PDL", 1);
   if (!enabled) return 0;
   attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr->val.programmaticStreamSerializationAllowed = 1;

@@ -18,8 +18,21 @@ int check_launch(const char* what);   // cudaGetLastError -> UDT_ERR_LAUNCH
 int require_sm100();                  // UDT_OK or UDT_ERR_ARCH (cached per device)
 int num_sms();
 int arch();                           // compute capability * 10 of the current device, or <0
+// Experiment switches.  A PRODUCTION build of this library reads no environment variable and has no hidden state: every
+// switch is the compile-time default below.  A TUNING build (`UDT_TRACE=1 python -m udifftext_b200.build`, which defines
+// UDT_TUNING) reads the named variable once, so that A/B measurements (scripts/) need no rebuild per variant.
+#ifdef UDT_TUNING
+#include <stdlib.h>
+inline int tune_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+#else
+inline constexpr int tune_int(const char*, int dflt) { return dflt; }
+#endif
+
 // Programmatic dependent launch (every kernel of this library executes griddepcontrol.wait before it touches
-// global memory): fills one launch attribute and returns 1, or returns 0 when disabled (UDT_PDL=0).
+// global memory): fills one launch attribute and returns 1, or returns 0 when disabled (tuning builds: UDT_PDL=0).
 int pdl_attr(cudaLaunchAttribute* attr);
 
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute

@@ -180,6 +180,9 @@ __device__ __forceinline__ void finish_columns(const IGemmParams& p, float (&f)[
   } else if (p.act == UDT_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (p.act == UDT_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
   }
   if (p.out_fp32) {
     float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(split) * p.split_stride + m * p.ldo + col;
@@ -610,6 +613,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
             } else if (p.act == UDT_ACT_RELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            } else if (p.act == UDT_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
             }
           }
         }
@@ -969,11 +975,6 @@ int launch_igemm(const IGemmParams& p, int grid, int smem, cudaStream_t st) {
 
 extern "C" int udt_geglu_tile(void) { return kGegluTile; }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 extern "C" int udt_debug_set_trace(void* buf, int64_t nbytes) {
   if (!kTraceBuild) return 0;   // production build: tracing is compiled out (rebuild with UDT_TRACE=1)
   g_trace_buf = reinterpret_cast<unsigned long long*>(buf);
@@ -1036,7 +1037,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   int ksteps_est = 0;
   for (int s = 0; s < nsrc; ++s) ksteps_est += d->src[s].taps * ((d->src[s].C + 63) / 64);
   // CTA pairs (tcgen05 cta_group::2) whenever there are at least two M tiles and a real column tile
-  static const int pair_env = env_int("UDT_IGEMM_PAIR", 1);
+  static const int pair_env = udt_host::tune_int("UDT_IGEMM_PAIR", 1);
   bool pair = pair_env != 0 && tiles_m >= 2 && N_out > 16 && sms >= 2;
   int BN = geglu_tile > 0 ? geglu_tile : (d->bn_hint > 0 ? d->bn_hint : pick_bn(N_out, tiles_m, ksteps_est, pair, sms));
   if (BN != 16 && (BN % 32 != 0 || BN < 32 || BN > 256)) return fail(UDT_ERR_SHAPE, "udt_igemm: BN=%d unsupported", BN);
@@ -1044,7 +1045,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
   // split-K: a small-M problem (few tiles, long K) streams its weights with every SM by splitting the K range; the
   // fp32 partial tiles go to the caller's workspace and a second kernel reduces them and applies the epilogue
   int ksplit = 1, kper = ksteps_est;
-  static const int split_env = env_int("UDT_IGEMM_SPLITK", 1);
+  static const int split_env = udt_host::tune_int("UDT_IGEMM_SPLITK", 1);
   if (split_env != 0 && d->bn_hint == 0 && act == UDT_ACT_NONE && !d->out_fp32 && d->workspace != nullptr && N_out % 8 == 0 &&
       d->out_stride_w == 0 && d->weight_img_rows == 0 &&
       N_out >= 64 && d->ldo % 8 == 0 && (d->residual == nullptr || d->ldr % 8 == 0) &&
@@ -1191,11 +1192,7 @@ extern "C" int udt_igemm(const udt_igemm_desc* d, void* stream) {
     p.residual = nullptr;
   }
 
-  static int dbg = -1;
-  if (dbg < 0) {
-    const char* e = getenv("UDT_IGEMM_DEBUG");
-    dbg = e ? atoi(e) : 0;
-  }
+  static const int dbg = udt_host::tune_int("UDT_IGEMM_DEBUG", 0);
   p.debug = dbg;
   p.trace = nullptr;
   if (dbg & 0xF00) {

@@ -757,10 +757,7 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
   a.groups = groups;
   a.silu = silu;
   a.eps = eps;
-  static const bool onepass_ok = [] {
-    const char* e = getenv("UDT_GN_ONEPASS");
-    return e == nullptr || atoi(e) != 0;
-  }();
+  static const bool onepass_ok = udt_host::tune_int("UDT_GN_ONEPASS", 1) != 0;
   // largest usable cluster: 16 CTAs (non-portable size) when the device can co-schedule such a cluster with the
   // kernel's full shared-memory footprint, else the portable 8
   static int max_cluster = 0;
@@ -768,12 +765,9 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
     cudaError_t e = cudaFuncSetAttribute(gn_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
     if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(gn one-pass smem): %s", cudaGetErrorString(e));
     max_cluster = 8;
-    static const bool big_ok = [] {
-      // opt-in: measured SLOWER than the two-pass schedule on B200 (8 co-resident clusters of 16 CTAs pull a 2.6 MB sample
-      // at single-SM rates: 64x64x320 28 us vs 19 us), kept for experiments
-      const char* e2 = getenv("UDT_GN_CLUSTER16");
-      return e2 != nullptr && atoi(e2) != 0;
-    }();
+    // opt-in (tuning builds): measured SLOWER than the two-pass schedule on B200 (8 co-resident clusters of 16 CTAs pull a
+    // 2.6 MB sample at single-SM rates: 64x64x320 28 us vs 19 us), kept for experiments
+    static const bool big_ok = udt_host::tune_int("UDT_GN_CLUSTER16", 0) != 0;
     if (big_ok && cudaFuncSetAttribute(gn_onepass_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       cudaLaunchConfig_t q;
       memset(&q, 0, sizeof(q));
@@ -793,14 +787,9 @@ extern "C" int udt_groupnorm_nhwc(const void* x0, int32_t C0, const void* x1, in
     (void)cudaGetLastError();
   }
   // group-owner schedule while the whole tensor is L2 resident (UDT_GN_GROUP=0: never)
-  static const bool group_ok = [] {
-    const char* e = getenv("UDT_GN_GROUP");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  static const size_t group_limit = [] {      // tensor size up to which the group-owner schedule is used (UDT_GN_GROUP_MB)
-    const char* e = getenv("UDT_GN_GROUP_MB");
-    return static_cast<size_t>(e ? atoi(e) : 64) << 20;
-  }();
+  static const bool group_ok = udt_host::tune_int("UDT_GN_GROUP", 1) != 0;
+  // tensor size up to which the group-owner schedule is used (tuning builds: UDT_GN_GROUP_MB)
+  static const size_t group_limit = static_cast<size_t>(udt_host::tune_int("UDT_GN_GROUP_MB", 64)) << 20;
   {
     const int cpg = C / groups;
     const size_t bytes = static_cast<size_t>(NB) * HW * C * 2;

@@ -14,8 +14,13 @@ class FullLoss:
                  lambda_ocr_loss=0.0, lambda_style_loss=0.0, ocr_enabled=False, style_enabled=False,
                  predictor_config=None, sigma_sampler_config=None, type="l2", offset_noise_level=0.0,
                  batch2model_keys=None, **unused):
-        if ocr_enabled:
-            raise NotImplementedError("OCR loss (PARSeq) is a training / evaluation component and out of scope")
+        # the OCR loss term (loss.py:150-160) belongs to training; the predictor itself is available for evaluation
+        # (host/predictor.py) and is instantiated here only to honour `predictor_config` of the model YAML
+        self.ocr_enabled = bool(ocr_enabled)
+        self.predictor = None
+        if ocr_enabled and predictor_config is not None:
+            from .config import instantiate_from_config
+            self.predictor = instantiate_from_config(predictor_config)
         self.gaussian_kernel_size = kernel_size
         self.min_attn_size = min_attn_size
         self.g_kernel = self.get_gaussian_kernel(kernel_size, gaussian_sigma, seq_len)

@@ -2,7 +2,7 @@
 implementations without requiring the drop-in `sgm` package to shadow anything on sys.path."""
 from __future__ import annotations
 
-from . import autoencoder, conditioner, engine, loss, network, sampler, schedule
+from . import autoencoder, conditioner, engine, loss, network, predictor, sampler, schedule
 
 TARGETS = {
     "sgm.models.diffusion.DiffusionEngine": engine.DiffusionEngine,
@@ -27,5 +27,6 @@ TARGETS = {
     "sgm.modules.diffusionmodules.sigma_sampling.DiscreteSampling": schedule.DiscreteSampling,
     "sgm.modules.diffusionmodules.sampling.EulerEDMSampler": sampler.EulerEDMSampler,
     "sgm.modules.diffusionmodules.loss.FullLoss": loss.FullLoss,
+    "sgm.modules.predictors.model.ParseqPredictor": predictor.ParseqPredictor,
     "torch.nn.Identity": __import__("torch").nn.Identity,
 }

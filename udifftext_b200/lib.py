@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_vo
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libudt_b200.so")
 
-UDT_ACT_NONE, UDT_ACT_SILU, UDT_ACT_GEGLU, UDT_ACT_RELU = 0, 1, 2, 3
+UDT_ACT_NONE, UDT_ACT_SILU, UDT_ACT_GEGLU, UDT_ACT_RELU, UDT_ACT_GELU = 0, 1, 2, 3, 4
 
 
 class UdtError(RuntimeError):
@@ -66,6 +66,8 @@ _PROTOTYPES = {
     "udt_mha_small_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                     c_void_p]),
     "udt_mha_small": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "udt_mha_masked": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                 c_int32, c_int32, c_int32, c_float, c_void_p, c_int32, c_void_p, c_void_p]),
     "udt_softmax_rows": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
     "udt_xattn_fold": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32,
                                  c_int32, c_int32, c_int32, c_float, c_void_p]),
@@ -77,8 +79,6 @@ _PROTOTYPES = {
     "udt_pointwise_affine": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_float, c_void_p]),
     "udt_upsample2x_nhwc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
-    "udt_im2col3x3_nhwc": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
-                                     c_int32, c_int32, c_int32, c_void_p]),
     "udt_nchw_f32_to_nhwc_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "udt_nhwc_to_nchw_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
                                        c_int32, c_void_p]),

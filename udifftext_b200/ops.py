@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import lib as _lib
-from .lib import UDT_ACT_GEGLU, UDT_ACT_NONE, UDT_ACT_RELU, UDT_ACT_SILU, GemmSrc, IGemmDesc  # noqa: F401
+from .lib import UDT_ACT_GEGLU, UDT_ACT_GELU, UDT_ACT_NONE, UDT_ACT_RELU, UDT_ACT_SILU, GemmSrc, IGemmDesc  # noqa: F401
 
 
 _launches = 0   # C-ABI compute calls issued by this process (each is one or two kernel launches of libudt_b200)
@@ -320,14 +320,12 @@ def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] 
 
 
 def conv3x3_up2(x: torch.Tensor, weights4: Sequence[torch.Tensor], bias: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None, w_full: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nearest-2x upsample + 3x3 conv (pad 1) of NHWC fp16 `x` [nb, h, w, c] -> [nb, 2h, 2w, n] as four 2x2-window implicit
     GEMMs on the low-resolution input, one per output phase (`weights4` from pack.pack_conv3x3_up2): 2.25x fewer FLOPs
     than materialising the upsampled tensor, and no upsample kernel."""
     nb, h, w, c = x.shape
     n = weights4[0].shape[0]
-    if w_full is not None and os.environ.get("UDT_UP2", "1") == "0":      # A/B switch (tuning): materialised upsample
-        return conv3x3(upsample2x(x), w_full, bias, out=out)
     if out is None:
         out = torch.empty((nb, 2 * h, 2 * w, n), device=x.device, dtype=torch.float16)
     sw, sh, sn = 2 * n, 2 * (2 * w) * n, (2 * h) * (2 * w) * n
@@ -493,6 +491,23 @@ def mha_small(qkv: torch.Tensor, b: int, l: int, heads: int, out: Optional[torch
     return out
 
 
+def mha_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, lq: int, lk: int, heads: int,
+               mask: Optional[torch.Tensor] = None, kpm: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q fp16 [B*Lq, >= D], k / v fp16 [B*Lk, >= D] (2-D views, unit column stride) -> fp16 [B*Lq, D]; mask fp32 [Lq, Lk]
+    additive, kpm uint8 [B, Lk] (udt_mha_masked; softmax scale = head_dim^-0.5)"""
+    d = q.shape[1]
+    dh = d // heads
+    if out is None:
+        out = torch.empty((b * lq, d), device=q.device, dtype=torch.float16)
+    assert mask is None or (mask.dtype == torch.float32 and mask.stride(1) == 1 and tuple(mask.shape) == (lq, lk))
+    assert kpm is None or (kpm.dtype == torch.uint8 and kpm.is_contiguous() and tuple(kpm.shape) == (b, lk))
+    _invoke("udt_mha_masked", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, lq, lk, heads, dh, q.stride(0),
+            k.stride(0), v.stride(0), out.stride(0), float(dh) ** -0.5, _ptr(mask), 0 if mask is None else mask.stride(0),
+            _ptr(kpm))
+    return out
+
+
 def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
     rows, cols = x.shape
     _invoke("udt_softmax_rows", x.data_ptr(), rows, cols, x.stride(0), float(scale))
@@ -546,15 +561,6 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     if out is None:
         out = torch.empty((nb, 2 * h, 2 * w, c), device=x.device, dtype=torch.float16)
     _invoke("udt_upsample2x_nhwc", x.data_ptr(), out.data_ptr(), nb, h, w, c)
-    return out
-
-
-def im2col3x3(x: torch.Tensor, stride: int, pad_lo: int, ho: int, wo: int, kpad: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    nb, h, w, c = x.shape
-    if out is None:
-        out = torch.empty((nb * ho * wo, kpad), device=x.device, dtype=torch.float16)
-    _invoke("udt_im2col3x3_nhwc", x.data_ptr(), out.data_ptr(), nb, h, w, c, x.stride(2), stride, pad_lo, ho, wo, kpad)
     return out
 
 

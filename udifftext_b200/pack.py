@@ -39,14 +39,6 @@ def pack_conv3x3(w_oihw: torch.Tensor, skip_1x1: Sequence[torch.Tensor] = (), ci
     return torch.cat(parts, dim=1).to(torch.float16).contiguous()
 
 
-def pack_conv3x3_padded(w_oihw: torch.Tensor, kpad: int) -> torch.Tensor:
-    """explicit-im2col variant (udt_im2col3x3_nhwc): K = 9*I (tap, channel) zero padded to `kpad` (multiple of 64)."""
-    o, i, _, _ = w_oihw.shape
-    out = torch.zeros((o, kpad), dtype=torch.float16, device=w_oihw.device)
-    out[:, : 9 * i] = w_oihw.permute(0, 2, 3, 1).reshape(o, 9 * i).to(torch.float16)
-    return out
-
-
 def pack_conv3x3_up2(w_oihw: torch.Tensor) -> list:
     """nearest-2x upsample followed by a 3x3 conv (pad 1) == four 2x2 convs on the LOW-resolution input, one per output
     phase (py, px): output pixel (2h+py, 2w+px) reads source rows {h-1, h} (py = 0) or {h, h+1} (py = 1), and the 3x3 taps

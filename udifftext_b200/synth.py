@@ -42,6 +42,45 @@ ARCH = {
 }
 
 
+PARSEQ_ARCH = dict(img_size=(32, 128), patch_size=(4, 8), embed_dim=384, enc_num_heads=6, enc_mlp_ratio=4, enc_depth=12,
+                   dec_num_heads=12, dec_mlp_ratio=4, dec_depth=1, max_label_length=25, num_tokens=97)
+
+
+def parseq_manifest(arch: Optional[dict] = None) -> Dict[str, List[int]]:
+    """state_dict layout (key -> shape) of the PARSeq checkpoint `parseq-bb5792a6.pt` that ParseqPredictor loads
+    (configs/test.yaml:34): timm ViT encoder + one two-stream decoder layer + head (src/parseq/strhub/models/parseq)"""
+    a = dict(PARSEQ_ARCH, **(arch or {}))
+    d, ph, pw = a["embed_dim"], a["patch_size"][0], a["patch_size"][1]
+    n = (a["img_size"][0] // ph) * (a["img_size"][1] // pw)
+    m: Dict[str, List[int]] = {"encoder.pos_embed": [1, n, d], "encoder.patch_embed.proj.weight": [d, 3, ph, pw],
+                               "encoder.patch_embed.proj.bias": [d]}
+
+    def lin(name, o, i):
+        m[name + ".weight"], m[name + ".bias"] = [o, i], [o]
+
+    def ln(name):
+        m[name + ".weight"], m[name + ".bias"] = [d], [d]
+
+    for i in range(a["enc_depth"]):
+        p = f"encoder.blocks.{i}."
+        ln(p + "norm1"); lin(p + "attn.qkv", 3 * d, d); lin(p + "attn.proj", d, d); ln(p + "norm2")
+        lin(p + "mlp.fc1", a["enc_mlp_ratio"] * d, d); lin(p + "mlp.fc2", d, a["enc_mlp_ratio"] * d)
+    ln("encoder.norm")
+    for i in range(a["dec_depth"]):
+        p = f"decoder.layers.{i}."
+        for att in ("self_attn", "cross_attn"):
+            m[p + att + ".in_proj_weight"], m[p + att + ".in_proj_bias"] = [3 * d, d], [3 * d]
+            lin(p + att + ".out_proj", d, d)
+        lin(p + "linear1", a["dec_mlp_ratio"] * d, d); lin(p + "linear2", d, a["dec_mlp_ratio"] * d)
+        for nm in ("norm1", "norm2", "norm_q", "norm_c"):
+            ln(p + nm)
+    ln("decoder.norm")
+    lin("head", a["num_tokens"] - 2, d)
+    m["text_embed.embedding.weight"] = [a["num_tokens"], d]
+    m["pos_queries"] = [1, a["max_label_length"] + 1, d]
+    return m
+
+
 def load_manifest(name: str) -> Dict[str, List[int]]:
     with open(os.path.join(MANIFEST_DIR, f"{name}.json")) as f:
         return json.load(f)
@@ -82,6 +121,8 @@ def synthetic_state_dict(manifest: Dict[str, List[int]], seed: int = 1234) -> Di
             t = _sinusoid_pe(shape[0], shape[1])
         elif key == "loss_fn.g_kernel":
             t = _gauss_kernel(shape[0], shape[2])
+        elif leaf in ("pos_embed", "pos_queries") or key.endswith("text_embed.embedding.weight"):
+            t = torch.randn(shape, generator=g) * (0.5 if leaf != "weight" else 0.05)       # PARSeq tables
         elif len(shape) >= 2:
             fan_in = int(np.prod(shape[1:]))
             std = 1.0 if "label_embedding" in key else 1.0 / math.sqrt(fan_in)

@@ -63,6 +63,15 @@ class _VAttn:
         self.b_v = pack.f32(sd[p + "v.bias"]).to(dev)                     # added after P V
         self.w_o = pack.pack_linear(sd[p + "proj_out.weight"]).to(dev)
         self.b_o = pack.f32(sd[p + "proj_out.bias"]).to(dev)
+        self._wv_tiled: dict = {}
+
+    def w_v_tiled(self, nb: int) -> torch.Tensor:
+        """W_v stacked nb times: the A operand of the batched V^T GEMM (rows [i*c, (i+1)*c) multiply image i's pixels)"""
+        t = self._wv_tiled.get(nb)
+        if t is None:
+            t = self.w_v.repeat(nb, 1).contiguous()
+            self._wv_tiled[nb] = t
+        return t
 
 
 class VAEB200:
@@ -126,8 +135,7 @@ class VAEB200:
             item = {"blocks": blocks, "up": None}
             k = f"decoder.up.{lvl}.upsample.conv."
             if k + "weight" in sd:
-                item["up"] = ([t.to(dev) for t in pack.pack_conv3x3_up2(sd[k + "weight"])], pack.f32(sd[k + "bias"]).to(dev),
-                              pack.pack_conv3x3(sd[k + "weight"]).to(dev))
+                item["up"] = ([t.to(dev) for t in pack.pack_conv3x3_up2(sd[k + "weight"])], pack.f32(sd[k + "bias"]).to(dev))
             self.d_up.append(item)
         self.d_g, self.d_b = pack.f32(sd["decoder.norm_out.weight"]).to(dev), pack.f32(sd["decoder.norm_out.bias"]).to(dev)
         self.d_w_out = pack.pack_conv3x3(sd["decoder.conv_out.weight"]).to(dev)
@@ -154,20 +162,31 @@ class VAEB200:
         return ops.conv3x3(a2, r.w2, r.cb2, residual=x)
 
     def _attn(self, a: _VAttn, x: torch.Tensor) -> torch.Tensor:
+        """single-head attention over the pixels (model.py:228-262), all images of the batch per launch: the per-image
+        operands K_i and V_i^T enter udt_igemm as per-image WEIGHTS (weight_img_rows), so q k^T, the row softmax, V^T, P V and
+        proj_out are five launches for the whole batch (the N x N probabilities still pass through HBM as fp16 — d = 512
+        does not fit the TMEM budget of the fused d = 64 kernel)"""
         nb, hh, ww, c = x.shape
         n = hh * ww
         hn = self._gn(x, a.g, a.b, False).view(nb * n, c)
         qk = ops.linear(hn, a.w_qk, a.b_qk)                       # [nb*n, 2c]: q (pre-scaled) | k
-        out = torch.empty((nb * n, c), device=x.device, dtype=torch.float16)
         xf = x.view(nb * n, c)
-        for i in range(nb):                                       # N x N score matrix per image
-            rows = slice(i * n, (i + 1) * n)
-            s = ops.linear(qk[rows, :c], qk[rows, c:])            # q k^T  [n, n]
-            ops.softmax_rows_(s, 1.0)
-            vt = ops.linear(a.w_v, hn[rows])                      # V^T (without bias) [c, n]
-            o = ops.linear(s, vt, a.b_v)                          # P V + b_v  [n, c]
-            ops.linear(o, a.w_o, a.b_o, residual=xf[rows], out=out[rows])
-        return out.view(nb, hh, ww, c)
+        if n % 128 or nb == 1:                                    # ragged pixel count: one image at a time
+            out = torch.empty((nb * n, c), device=x.device, dtype=torch.float16)
+            for i in range(nb):
+                rows = slice(i * n, (i + 1) * n)
+                s = ops.linear(qk[rows, :c], qk[rows, c:])        # q k^T  [n, n]
+                ops.softmax_rows_(s, 1.0)
+                vt = ops.linear(a.w_v, hn[rows])                  # V^T (without bias) [c, n]
+                o = ops.linear(s, vt, a.b_v)                      # P V + b_v  [n, c]
+                ops.linear(o, a.w_o, a.b_o, residual=xf[rows], out=out[rows])
+            return out.view(nb, hh, ww, c)
+        s = ops.linear(qk[:, :c], qk[:, c:], groups=nb, weight_img_rows=n)          # q_i k_i^T  [nb*n, n]
+        ops.softmax_rows_(s, 1.0)
+        wv = a.w_v_tiled(nb)                                                        # W_v repeated per image  [nb*c, c]
+        vt = ops.linear(wv, hn, groups=nb, weight_img_rows=n)                       # V_i^T (without bias)  [nb*c, n]
+        o = ops.linear(s, vt, a.b_v, groups=nb, weight_img_rows=c)                  # P_i V_i + b_v  [nb*n, c]
+        return ops.linear(o, a.w_o, a.b_o, residual=xf).view(nb, hh, ww, c)
 
     # ------------------------------------------------------------------------------------------ encode
     def encode_moments_nhwc(self, x: torch.Tensor) -> torch.Tensor:
@@ -206,8 +225,8 @@ class VAEB200:
             for r in item["blocks"]:
                 h = self._res(r, h)
             if item["up"] is not None:                             # nearest x2 + conv3x3 (model.py:55-68)
-                w4, b, wf = item["up"]
-                h = ops.conv3x3_up2(h, w4, b, w_full=wf)                      # four 2x2 phase convs on the low-res tensor
+                w4, b = item["up"]
+                h = ops.conv3x3_up2(h, w4, b)                                 # four 2x2 phase convs on the low-res tensor
         a = self._gn(h, self.d_g, self.d_b, True)
         nb, oh, ow, _ = a.shape
         out = torch.empty((nb, oh, ow, 4), device=self.device, dtype=torch.float32)
