@@ -18,4 +18,5 @@ UDT_NCU_NB=64 UDT_NCU_REPS=1 timeout 900 ncu --set full --import-source on --clo
 echo "full set rc=$?"
 python scripts/ncu_summary.py "$OUT/r02_full_b32.ncu-rep" "$OUT/r02_ncu_full_summary_b32.csv"
 ncu -i "$OUT/r02_full_b32.ncu-rep" --page details --csv > "$OUT/r02_ncu_full_details_b32.csv" 2>/dev/null
+rm -f "$OUT/r02_full_b32.ncu-rep"      # 70+ MB: only its CSV exports travel back (gpurun_out is capped at 64 MiB)
 ls -la "$OUT" | tail -12

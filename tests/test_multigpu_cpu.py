@@ -38,6 +38,11 @@ def _worker(rank, world, port, gb, out_dir):
     with rng.batch_shard(gb, lo, hi):
         img = _fake_predict(mine, (hi - lo, 4, 2, 2))
     gathered = api.all_gather_images(img, gb)
+    # what bench.py gathers: the uint8 HWC images (udt_images_to_u8 on the GPU; the same expression here), ragged shards too
+    u8 = (img.clamp(0, 1).permute(0, 2, 3, 1) * 255).to(torch.uint8).contiguous()
+    g8 = api.all_gather_images(u8, gb)
+    assert g8.dtype == torch.uint8 and tuple(g8.shape) == (gb, 16, 16, 3)
+    assert torch.equal(g8, (gathered.clamp(0, 1).permute(0, 2, 3, 1) * 255).to(torch.uint8))
     torch.save(gathered, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
