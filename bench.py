@@ -47,10 +47,14 @@ def measured_peaks():
     return {"tflops": 1590.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md: 1.59 PFLOP/s, 6.65 TB/s)"}
 
 
-def ncu_traffic_per_launch():
+def ncu_traffic_per_launch(batch: int = 4):
     """dram__bytes_read.sum + dram__bytes_write.sum per udt_igemm launch (average over the launches of one UNet CFG step),
-    from the committed ncu capture of scripts/ncu_step.py (profiles/r01_step_igemm_traffic.json); None if absent"""
-    path = os.path.join(ROOT, "profiles", "r01_step_igemm_traffic.json")
+    from the committed ncu capture of scripts/ncu_step.py at that batch size (profiles/r01_step_igemm_traffic.json for
+    BASELINE configs[1], profiles/r02_step_igemm_traffic_b32.json for configs[2]); None for any other batch"""
+    name = {4: "r01_step_igemm_traffic.json", 32: "r02_step_igemm_traffic_b32.json"}.get(batch)
+    if name is None:
+        return None
+    path = os.path.join(ROOT, "profiles", name)
     try:
         with open(path) as f:
             return float(json.load(f)["dram_bytes_per_launch"])
@@ -323,7 +327,7 @@ def run_b200(args):
         else:        # fallback: each shape replayed alone -> burst clocks, L2-warm: compare with the burst peak
             ach, peak, how, ms_used = alone, peaks["tflops_burst"], "each shape replayed alone vs bf16_tflops (burst)", ig["ms"]
         roofline = {"bound": "tensor", "kernel": "udt_igemm_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": ncu_traffic_per_launch(), "peak_source": peaks["source"], "method": how,
+                    "frac": ach / peak, "traffic": ncu_traffic_per_launch(B), "peak_source": peaks["source"], "method": how,
                     "launches_per_unet_step": ig["calls"], "ms_per_unet_step": ms_used,
                     "avg_launch_us": 1e3 * ms_used / max(ig["calls"], 1), "flop_per_launch": flops / max(ig["calls"], 1),
                     "share_of_step": (igg["ms"] / profg["step_ms_graph_with_events"]) if igg else ig["ms"] / max(prof["step_ms_eager_sum"], 1e-9),

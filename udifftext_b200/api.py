@@ -28,7 +28,8 @@ def model_config(arch: str = "full") -> AttrDict:
            "params": {"embed_dim": 4, "monitor": "val/rec_loss", "lossconfig": {"target": "torch.nn.Identity"},
                       "ddconfig": dict(attn_type="vanilla-xformers", double_z=True, resolution=256, attn_resolutions=[],
                                        dropout=0.0, **a["vae"])}}
-    unet = dict(a["unet"], ctrl_channels=0, save_attn_type=["t_attn"], save_attn_layers=["output_blocks.6.1"],
+    unet = dict(a["unet"], ctrl_channels=0, save_attn_type=["t_attn"],
+                save_attn_layers=["output_blocks.6.1" if arch == "full" else "output_blocks.3.1"],
                 use_linear_in_transformer=True)
     cfg = {"target": "sgm.models.diffusion.DiffusionEngine", "params": {
         "opt_keys": ["t_attn"], "input_key": "image", "scale_factor": a["scale_factor"], "disable_first_stage_autocast": True,
