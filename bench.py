@@ -36,6 +36,19 @@ GFLOP_UNET_IGEMM = 394.78 + 5.66 + 18.04 + 257.14   # conv3x3 + conv3x3-s2 + con
 GFLOP_VAE_ENC, GFLOP_VAE_DEC = 1116.7, 2514.5
 
 
+def workload_name(batch: int, world: int = 1) -> str:
+    """the `config.workload` string of both arms (identical text, so that the two lines can be matched)"""
+    tag = ""
+    if world == 1:
+        tag = {4: " (BASELINE configs[1])", 32: " (BASELINE configs[2])"}.get(batch, "")
+    elif batch == 4:
+        tag = " (BASELINE configs[1] per GPU)"
+    elif (batch, world) == (8, 8):
+        tag = " (BASELINE configs[3])"
+    return (f"batch {batch} per GPU, {IMG}x{IMG}, {DDIM_STEPS} DDIM steps (EulerEDM+LegacyDDPM, CFG 5.0), "
+            f"{LABEL_LEN}-char strings, noise_iters 0{tag}")
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -148,7 +161,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * PER_GPU_BATCH / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"batch {PER_GPU_BATCH}, {IMG}x{IMG}, {DDIM_STEPS} DDIM steps, {LABEL_LEN}-char strings (BASELINE configs[1])",
+            "config": {"workload": workload_name(PER_GPU_BATCH, max(1, args.gpus)),
                        "note": "reference algorithm (fp32 PyTorch restatement, oracle/restated.py) on host CPU cores"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
                              "detail": timed[-1]},
@@ -346,13 +359,10 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        cfg_name = {4: " (BASELINE configs[1])", 32: " (BASELINE configs[2])"}.get(B, "") if world == 1 else \
-            (" (BASELINE configs[1] per GPU)" if B == 4 else (" (BASELINE configs[3])" if (B, world) == (8, 8) else ""))
         line = {"metric": "512x512 50-step DDIM images/sec", "value": m["value"], "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate)", "data": "synthetic",
-                "config": {"workload": f"batch {B} per GPU, {IMG}x{IMG}, {DDIM_STEPS} DDIM steps (EulerEDM+LegacyDDPM, CFG 5.0), "
-                                       f"{LABEL_LEN}-char strings, noise_iters 0{cfg_name}",
+                "config": {"workload": workload_name(B, world),
                            "global_batch": m["gb"], "parallelism": f"batch-sharded x{world}, one all-gather of decoded uint8 images",
                            "l2": "working set per step >> 126 MB L2 (1.78 GB fp16 UNet weights streamed every step); no explicit flush",
                            "weights": "seeded synthetic, exact SD-2-inpainting UNifiedUNet / AutoencoderKL / LabelEncoder architecture",
