@@ -399,6 +399,299 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
 }
 
 
+
+#ifdef UDT_TUNING
+// ------------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (tuning builds only, UDT_FMHA_W4=1) — measured on B200: correct (same errors to 4 digits incl. replay and ragged
+// tiles) and 7 % SLOWER than the two-warpgroup kernel (4096 tokens 244 -> 260 us, 1024 tokens 45.2 -> 49.1 us): the kernel is
+// not limited by the number of warps a scheduler can pick from.
+// Four softmax warpgroups: every 128x128 score tile is shared by TWO warpgroups, each thread owns one query row and HALF of
+// the tile's keys (64 columns).  Why: ncu shows the two-warpgroup kernel with 2.5 active warps per scheduler of which 0.57
+// are eligible (58 % of the cycles no warp can issue) — the tcgen05.ld -> FMA -> MUFU -> pack chain of one row of 128 keys
+// is latency-bound with two warps per sub-partition.  Twice the warps on the same tensor-memory lanes (warp w and w + 4 share
+// lanes 32 * (w % 4)) halve the chain per thread and double the warps a scheduler can pick from; registers per thread drop
+// from 168 to <= 112 (32 packed probabilities instead of 64).
+//   warps 0-3 / 4-7    : tile 0, keys [0, 64) / [64, 128) of every key tile        warp 16 : MMA issuer
+//   warps 8-11 / 12-15 : tile 1, keys [0, 64) / [64, 128)                          warp 17 : TMA producer
+// The two halves of a row agree once per key tile through a 64-thread named barrier + two shared-memory words: whether the
+// optimistic single pass violated the 2^8 bound (then both replay), the row maximum of a replayed / first tile, and at the
+// end the two partial row sums.  Each half writes its probabilities over score columns it has itself consumed — keys
+// [0, 64) -> columns [0, 32), keys [64, 128) -> columns [64, 96) — so no half ever overwrites scores the other still reads;
+// the PV MMA reads its A operand from those two column ranges.
+constexpr int kW4Threads = 576;
+constexpr int kW4OffX = 1024;                       // exchange area: [2 parity][2 tiles][2 halves][128 rows] floats + flags
+constexpr int kW4XBytes = 2 * 2 * 2 * 128 * 4 + 256;
+constexpr int kW4OffQ = 6144;                       // 1024-aligned operand tiles start here
+constexpr int kW4OffK = kW4OffQ + 2 * kTileBytes;
+constexpr int kW4OffV = kW4OffK + kKvStages * kTileBytes;
+constexpr int kW4SmemBytes = kW4OffV + kKvStages * kTileBytes + 1024;
+static_assert(kW4OffX + kW4XBytes <= kW4OffQ, "exchange area overlaps the Q tiles");
+
+__global__ void __launch_bounds__(kW4Threads, 1) udt_fmha_w4_kernel(const __grid_constant__ FmhaParams p) {
+  griddep_launch();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base = smem_raw + (base_addr - raw_addr);
+
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(base + kOffCtrl);
+  uint64_t* kv_full = q_full + 1;              // [kKvStages]
+  uint64_t* kv_empty = kv_full + kKvStages;    // [kKvStages]
+  uint64_t* s_full = kv_empty + kKvStages;     // [kSBufs]
+  uint64_t* p_full = s_full + kSBufs;          // [2]  both halves of P_t(j) are in tensor memory (256 arrivals)
+  uint64_t* o_full = p_full + 2;               // [2]  P_t(j) V_j has been accumulated into O_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* xval = reinterpret_cast<float*>(base + kW4OffX);                    // [parity][tile][half][row]
+  int* xflag = reinterpret_cast<int*>(base + kW4OffX + 2 * 2 * 2 * 128 * 4);   // [parity][tile][half][quarter]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int b, h, q0, ntiles;
+  if (!fmha_work(p, b, h, q0, ntiles)) return;
+  const int nkv = (p.Nkv + kTile - 1) / kTile;
+  const int ncomp = nkv * ntiles;
+
+  if (warp == 17 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < kSBufs; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 256);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+
+  if (warp == 17) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int col = h * kD;
+      mbar_expect_tx(q_full, static_cast<uint32_t>(ntiles * kTileBytes));
+      for (int t = 0; t < ntiles; ++t)
+        tma_load_2d(&p.mapQ, q_full, base + kW4OffQ + t * kTileBytes, col, b * p.Nq + q0 + t * kTile);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1u);
+        mbar_expect_tx(&kv_full[s], 2u * kTileBytes);
+        tma_load_2d(&p.mapK, &kv_full[s], base + kW4OffK + s * kTileBytes, col, b * p.Nkv + j * kTile);
+        tma_load_2d(&p.mapV, &kv_full[s], base + kW4OffV + s * kTileBytes, col, b * p.Nkv + j * kTile);
+        if (++s == kKvStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const bool issuer = elect_one();
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
+    auto issue_s = [&](const CompCursor& k) {
+      if (k.t == 0) mbar_wait(&kv_full[k.stage], static_cast<uint32_t>(k.kvphase));
+      tc_fence_after();
+      if (issuer) {
+        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kW4OffQ + k.t * kTileBytes);
+        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kW4OffK + k.stage * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk)
+          umma_f16_ss(tmem_base + kColS + k.b * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
+                      idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&s_full[k.b]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    CompCursor ks, kp;
+    ks.init();
+    kp.init();
+    for (int i = 0; i < kSBufs && ks.c < ncomp; ++i) {
+      issue_s(ks);
+      ks.advance(ntiles);
+    }
+    for (; kp.c < ncomp; kp.advance(ntiles)) {
+      mbar_wait(&p_full[kp.t], static_cast<uint32_t>(kp.j & 1));
+      tc_fence_after();
+      if (issuer) {
+        const uint32_t v_addr = base_addr + kW4OffV + kp.stage * kTileBytes;
+        const uint32_t p_tmem = tmem_base + kColS + kp.b * 128;
+#pragma unroll
+        for (int kk = 0; kk < kTile / 16; ++kk) {
+          const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
+          // keys [0, 64) of P live in columns [0, 32), keys [64, 128) in columns [64, 96) (8 columns per 16 keys)
+          const uint32_t pa = p_tmem + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
+          umma_f16_ts(tmem_base + kColO + kp.t * 64, pa, dv, idesc_o, (kp.j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[kp.t]);
+        if (kp.t == ntiles - 1) umma_commit(&kv_empty[kp.stage]);
+      }
+      __syncwarp();
+      if (ks.c < ncomp) {
+        issue_s(ks);
+        ks.advance(ntiles);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups (thread = row x half of the keys)
+    const int t = warp >> 3;           // query tile
+    const int half = (warp >> 2) & 1;  // key half of every tile
+    if (t < ntiles) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t o_addr = tmem_base + lane_base + kColO + t * 64 + half * 32;   // this half rescales / writes 32 O columns
+      const uint32_t bar_id = 1u + static_cast<uint32_t>(t * 4 + quarter);           // named barrier of this warp and its partner
+      const float sl2 = p.scale_log2;
+      float m_ref = -INFINITY, l = 0.0f;
+      int sb = t, su = 0;
+      // exchange slots, double buffered by tile parity (a warp is never two tiles ahead of its partner)
+      auto xv = [&](int par, int hf) -> float& { return xval[((par * 2 + t) * 2 + hf) * 128 + row]; };
+      auto xf = [&](int par, int hf) -> int& { return xflag[((par * 2 + t) * 2 + hf) * 4 + quarter]; };
+
+      auto rescale = [&](bool need, float m_tile, int j) {
+        const float m_new = need ? m_tile : m_ref;
+        const float alpha = need ? ex2_approx(m_ref - m_new) : 1.0f;
+        l *= alpha;
+        if (j > 0) {
+          mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));
+          tc_fence_after();
+          uint32_t v[32];
+          tmem_ld32(o_addr, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(o_addr, v);
+          tmem_st_wait();
+        }
+        m_ref = m_new;
+      };
+
+      for (int j = 0; j < nkv; ++j) {
+        const int par = j & 1;
+        mbar_wait(&s_full[sb], static_cast<uint32_t>(su & 1));
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_base + kColS + sb * 128 + half * 64;   // this half's 64 score columns
+        const int key_lim = p.Nkv - j * kTile - half * 64;   // my keys >= key_lim are padding (only on the last tile)
+        const bool partial = (p.Nkv - j * kTile) < kTile;    // uniform over both halves
+        float rowsum = 0.0f;
+        bool replay = (j == 0) || partial;
+        uint32_t pall[32];                                   // my 64 probabilities, fp16 pairs
+        if (!replay) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(s_addr, va);
+          tmem_ld_wait_dep(va);
+          tmem_ld32(s_addr + 32, vb);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(va[i]), sl2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(va[i + 1]), sl2, -m_ref));
+            rowsum += p0 + p1;
+            pall[i >> 1] = pack_half2(p0, p1);
+          }
+          tmem_ld_wait_dep(vb);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[i]), sl2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[i + 1]), sl2, -m_ref));
+            rowsum += p0 + p1;
+            pall[16 + (i >> 1)] = pack_half2(p0, p1);
+          }
+          // both halves of a row must agree: a violation in either sends both through the two-pass path
+          const bool viol = __any_sync(0xffffffffu, !(rowsum <= 256.0f));
+          if (lane == 0) xf(par, half) = viol ? 1 : 0;
+          named_bar_sync(bar_id, 64);
+          replay = (xf(par, 0) | xf(par, 1)) != 0;
+        }
+        if (replay) {
+          uint32_t v[32];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!partial || ch * 32 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          xv(par, half) = mx;
+          named_bar_sync(bar_id, 64);
+          const float m_tile = fmaxf(xv(par, 0), xv(par, 1)) * sl2;     // full-row maximum, identical in both halves
+          const bool need = m_tile > m_ref + kLazyThreshold;
+          if (__any_sync(0xffffffffu, need)) rescale(need, m_tile, j);
+          rowsum = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
+              if (partial) {
+                const int k0 = ch * 32 + i;
+                if (k0 >= key_lim) p0 = 0.0f;
+                if (k0 + 1 >= key_lim) p1 = 0.0f;
+              }
+              rowsum += p0 + p1;
+              pall[ch * 16 + (i >> 1)] = pack_half2(p0, p1);
+            }
+          }
+        }
+        l += rowsum;
+        // my P half -> the first 32 columns of my own (consumed) 64 score columns
+        tmem_st32(s_addr, pall);
+        tmem_st_wait();
+        if (j > 0) mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));   // observe every o_full phase
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        sb += ntiles;
+        if (sb >= kSBufs) { sb -= kSBufs; ++su; }
+      }
+      mbar_wait(&o_full[t], static_cast<uint32_t>((nkv - 1) & 1));
+      tc_fence_after();
+      // row sum = the two partial sums (both relative to the same reference maximum)
+      const int parE = nkv & 1;
+      xv(parE, half) = l;
+      named_bar_sync(bar_id, 64);
+      const float inv = 1.0f / (xv(parE, 0) + xv(parE, 1));
+      const int qrow = q0 + t * kTile + row;
+      uint4* o4 = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.Nq + min(qrow, p.Nq - 1)) * p.ldo + h * kD + half * 32);
+      uint32_t v[32];
+      tmem_ld32(o_addr, v);
+      tmem_ld_wait();
+      if (qrow < p.Nq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 ov;
+          ov.x = pack_half2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+          ov.y = pack_half2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+          ov.z = pack_half2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+          ov.w = pack_half2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+          o4[g] = ov;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+#endif  // UDT_TUNING
+
 }  // namespace
 
 extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t Nq, int32_t Nkv,
@@ -435,6 +728,20 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   dim3 grid(static_cast<unsigned>(p.pairs_full + 2 * (npairs - p.pairs_full)), 1, 1);
   // tuning builds: UDT_FMHA_POLY=4 moves every 4th exponential from MUFU to the FMA pipe.  Measured on B200: no gain
   // (4096 tokens 249.0 -> 250.4 us; every 2nd: 275 us) — the kernel is bound by the TMEM read path as much as by MUFU
+#ifdef UDT_TUNING
+  // experiment: four softmax warpgroups (two per score tile), UDT_FMHA_W4=1 — measured 7 % slower, see the kernel's header
+  static const int use_w4 = tune_int("UDT_FMHA_W4", 0);
+  if (use_w4) {
+    static bool w4_attr = false;
+    if (!w4_attr) {
+      cudaError_t e = cudaFuncSetAttribute(udt_fmha_w4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes);
+      if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha w4 smem): %s", cudaGetErrorString(e));
+      w4_attr = true;
+    }
+    udt_host::launch_pdl(udt_fmha_w4_kernel, dim3(grid), dim3(kW4Threads), kW4SmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
+    return check_launch("udt_fmha_fwd (w4)");
+  }
+#endif
   static const int poly = tune_int("UDT_FMHA_POLY", 0);
   void (*kern)(FmhaParams) = poly == 0 ? udt_fmha_ts_kernel<0> : udt_fmha_ts_kernel<4>;
   static bool ts_attr = false;
