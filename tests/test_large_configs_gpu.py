@@ -79,3 +79,30 @@ def test_c3_batch32_rows_are_shard_independent(full_engine):
     eo = _rel(z32[:4], zr)
     print(f"C3-shape predict: rows 0..4 vs fp32 oracle latents rel-L2 {eo:.3e}")
     assert eo < 2.6e-3   # 1.5 x measured (1.75e-3 after 2 steps)
+
+
+def test_full_size_non_square_matches_oracle(full_engine):
+    """full network on a 384x512 request (latent 48x64: 3072 / 768 / 192 / 48-token attentions, ragged FMHA tail, batched
+    VAE attention over 3072 pixels), batch 2 with a 1- and a 12-character label, 2 steps, vs the fp32 oracle"""
+    from oracle import restated as R
+    from udifftext_b200 import api, synth
+    eng, sd_dev = full_engine
+    dev = torch.device("cuda", 0)
+    cfgs = api.runtime_config(steps=2, batch_size=2)
+    sampler = api.init_sampling(cfgs)
+    sampler.verbose = False
+    batch = synth.synthetic_batch(8, 2, 384, 512, 4)
+    batch["label"] = ["Q", "UDiffText_12"]
+    batch["txt"] = [f'"{s}"' for s in batch["label"]]
+    batch["seg_mask"] = torch.stack([torch.cat((torch.ones(len(s)), torch.zeros(12 - len(s)))) for s in batch["label"]])
+    clone = lambda d: {k: (v.clone() if isinstance(v, torch.Tensor) else list(v)) for k, v in d.items()}
+    torch.manual_seed(61)
+    img, z = api.predict(cfgs, eng, sampler, clone(batch))
+    torch.cuda.synchronize()
+    torch.manual_seed(61)
+    with torch.no_grad():
+        ref_img, ref_z = R.predict(sd_dev, {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}, 2, 5.0)
+    ez, ep = _rel(z, ref_z), _rel(img, ref_img)
+    print(f"full 384x512 (2 steps): latents rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}")
+    assert tuple(img.shape) == (2, 3, 384, 512)
+    assert ez < 2.6e-3 and ep < 1.6e-3      # 1.5 x measured on B200 (1.69e-3 / 1.06e-3 after only 2 steps)

@@ -171,7 +171,7 @@ class VAEB200:
         hn = self._gn(x, a.g, a.b, False).view(nb * n, c)
         qk = ops.linear(hn, a.w_qk, a.b_qk)                       # [nb*n, 2c]: q (pre-scaled) | k
         xf = x.view(nb * n, c)
-        if n % 128 or nb == 1:                                    # ragged pixel count: one image at a time
+        if n % 256 or c % 256 or nb == 1:                         # per-image weights need whole CTA-pair tiles per image (256 rows)
             out = torch.empty((nb * n, c), device=x.device, dtype=torch.float16)
             for i in range(nb):
                 rows = slice(i * n, (i + 1) * n)
