@@ -106,3 +106,24 @@ def test_full_size_non_square_matches_oracle(full_engine):
     print(f"full 384x512 (2 steps): latents rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}")
     assert tuple(img.shape) == (2, 3, 384, 512)
     assert ez < 2.6e-3 and ep < 1.6e-3      # 1.5 x measured on B200 (1.69e-3 / 1.06e-3 after only 2 steps)
+
+
+def test_full_size_odd_batch_matches_oracle(full_engine):
+    """batch 3 (UNet batch 6: an odd number of images per CTA-pair tile row, ragged last wave), 512x512, 1 step"""
+    from oracle import restated as R
+    from udifftext_b200 import api, synth
+    eng, sd_dev = full_engine
+    dev = torch.device("cuda", 0)
+    cfgs = api.runtime_config(steps=1, batch_size=3)
+    sampler = api.init_sampling(cfgs)
+    sampler.verbose = False
+    batch = synth.synthetic_batch(13, 3, 512, 512, None)
+    torch.manual_seed(62)
+    img, z = api.predict(cfgs, eng, sampler, {k: (v.clone() if isinstance(v, torch.Tensor) else list(v)) for k, v in batch.items()})
+    torch.cuda.synchronize()
+    torch.manual_seed(62)
+    with torch.no_grad():
+        ref_img, ref_z = R.predict(sd_dev, {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}, 1, 5.0)
+    ez, ep = _rel(z, ref_z), _rel(img, ref_img)
+    print(f"full batch 3 (1 step): latents rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}")
+    assert ez < 2.4e-3 and ep < 1.6e-3      # 1.5 x measured on B200 (1.57e-3 / 1.02e-3 after ONE step)

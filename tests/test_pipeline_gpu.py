@@ -304,3 +304,34 @@ def test_edge_shapes_match_oracle(tiny_engine, hh, ww, lens, zero_uc):
     print(f"edge {hh}x{ww} lens {lens} zero_uc {zero_uc}: latents rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}")
     assert tuple(img.shape) == (b, 3, hh, ww)
     assert ez < 3.9e-3 and ep < 2.1e-3      # 1.5 x measured on B200 (2.6e-3 / 1.4e-3: the tiny network's 3-step fp16 floor)
+
+
+def test_generic_sampler_path_with_identity_guider(tiny_engine):
+    """a guider other than VanillaCFG disables the fused StepRunner: `__call__` and `get_init_noise` (noise_iters > 0) take
+    the generic per-op `sampler_step` loop of the reference (sampling.py:324-420).  IdentityGuider = no guidance: the result
+    must equal the oracle's Euler sampler with scale 1 (den = d_c)"""
+    from oracle import restated as R
+    from udifftext_b200 import api, synth
+    from udifftext_b200.host.sampler import EulerEDMSampler
+    dev = torch.device("cuda", 0)
+    sd = synth.synthetic_state_dict(synth.load_manifest("tiny"), 1234)
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    cfgs = api.runtime_config(steps=3, batch_size=1, noise_iters=2)
+    sampler = EulerEDMSampler(num_steps=3, discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"},
+                              guider_config=None, s_churn=0.0, s_tmin=0.0, s_tmax=999.0, s_noise=1.0, verbose=False, device=dev)
+    assert not sampler._fused_ok(tiny_engine)
+    batch = synth.synthetic_batch(71, 1, 64, 64, 5)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        dbatch, dbatch_uc = api.prepare_batch(cfgs, dict(batch))
+        c, uc = tiny_engine.conditioner.get_unconditional_conditioning(dbatch, batch_uc=dbatch_uc, force_uc_zero_embeddings=["label"])
+        best = sampler.get_init_noise(cfgs, tiny_engine, cond=c, batch=dbatch, uc=uc)       # generic noise search: runs, picks a drawn noise
+        assert tuple(best.shape) == (1, 4, 8, 8) and tuple(sampler.last_init_losses.shape) == (2, 1)
+        x0 = torch.randn((1, 4, 8, 8), generator=torch.Generator().manual_seed(9)).to(dev)
+        z = sampler(tiny_engine, x0.clone(), cond=c, batch=dbatch, uc=uc)
+        zr = R.euler_sample(R._sub(sd_dev, "model.diffusion_model."), x0.clone(), {k: v.float() for k, v in c.items()},
+                            {k: v.float() for k, v in uc.items()}, 3, 1.0)
+    torch.cuda.synchronize()
+    e = _rel(z, zr)
+    print(f"generic path (IdentityGuider) vs oracle scale 1: latents rel-L2 {e:.3e}")
+    assert e < 1.1e-3       # 1.5 x measured 7.25e-4 (no CFG amplification of the UNet error)
