@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 from udifftext_b200 import ops, synth
 from udifftext_b200.unet import UNetB200
 
-names = ["linear", "conv3x3", "groupnorm", "layernorm", "fmha", "xattn_small_l", "upsample2x", "im2col3x3"]
+names = ["linear", "conv3x3", "groupnorm", "layernorm", "fmha", "xattn_small_l", "upsample2x"]
 log = []
 orig = {n: getattr(ops, n) for n in names}
 def wrap(n):
