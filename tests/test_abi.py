@@ -64,3 +64,22 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions(udt_lib):
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "STTM"):
         assert mnemonic in sass, mnemonic
     assert "HMMA." not in sass.replace("UTCHMMA", "")  # no legacy mma.sync path
+
+
+def test_production_kernels_read_no_environment():
+    """every experiment switch goes through udt_host::tune_int, which reads the environment only in tuning builds
+    (-DUDT_TUNING); no other getenv exists in the kernel sources, and a default build does not define UDT_TUNING"""
+    import re
+    from udifftext_b200 import build
+    csrc = os.path.join(os.path.dirname(build.__file__), "csrc")
+    hits = []
+    for name in sorted(os.listdir(csrc)):
+        text = open(os.path.join(csrc, name)).read()
+        for m in re.finditer(r"\bgetenv\s*\(", text):
+            hits.append((name, text.count("\n", 0, m.start()) + 1))
+    assert [h[0] for h in hits] == ["udt_host.h"], hits
+    host_h = open(os.path.join(csrc, "udt_host.h")).read()
+    block = host_h[host_h.index("#ifdef UDT_TUNING"):host_h.index("#else", host_h.index("#ifdef UDT_TUNING"))]
+    assert "getenv" in block
+    os.environ.pop("UDT_TRACE", None)
+    assert "-DUDT_TUNING" not in build._flags()
