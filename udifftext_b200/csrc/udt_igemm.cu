@@ -582,11 +582,15 @@ __global__ void __launch_bounds__(kThreads, 1) udt_igemm_kernel(const __grid_con
           tmem_ld32(taddr + c0, v);
           tmem_ld32(taddr + p.BN / 2 + c0, vg);
           tmem_ld_wait();
+          const float* bgate = my_bias + p.BN / 2;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(v[j]) + my_bias[c0 + j];
-            const float gt = __uint_as_float(vg[j]) + my_bias[p.BN / 2 + c0 + j];
-            f[j] = x * gelu_erf_fast(gt);
+          for (int j = 0; j < 32; j += 4) {      // bias rows as 16-byte broadcast loads (the loop is issue-bound)
+            const float4 bx = *reinterpret_cast<const float4*>(my_bias + c0 + j);
+            const float4 bg = *reinterpret_cast<const float4*>(bgate + c0 + j);
+            f[j] = (__uint_as_float(v[j]) + bx.x) * gelu_erf_fast(__uint_as_float(vg[j]) + bg.x);
+            f[j + 1] = (__uint_as_float(v[j + 1]) + bx.y) * gelu_erf_fast(__uint_as_float(vg[j + 1]) + bg.y);
+            f[j + 2] = (__uint_as_float(v[j + 2]) + bx.z) * gelu_erf_fast(__uint_as_float(vg[j + 2]) + bg.z);
+            f[j + 3] = (__uint_as_float(v[j + 3]) + bx.w) * gelu_erf_fast(__uint_as_float(vg[j + 3]) + bg.w);
           }
         } else {
           if (!UDT_DBG(p, 8)) tmem_ld_wait_dep(v);   // this chunk's accumulators have landed in v[]
