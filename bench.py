@@ -170,6 +170,26 @@ def run_reference(args):
     args.emit(json.dumps(line))
 
 
+def executed_igemm(prof: dict, ms_used: float, peak: float):
+    """FLOPs the igemm launches of one step really EXECUTE (2 M N K of every launch as issued: zero-padded K blocks
+    included, the four-phase upsample convs and the folded / skipped t_attn of the unconditional half save work against the
+    reference's module graph) — the `achieved` figure above uses the reference's ALGORITHMIC FLOPs (effective throughput);
+    this one says how busy the tensor pipe has to be for it"""
+    flops = 0.0
+    for r in prof.get("by_shape", []):
+        if r["op"] != "udt_igemm":
+            continue
+        try:
+            m, n, k = (float(v) for v in r["shape"][:3])
+        except (ValueError, IndexError):
+            continue
+        flops += 2.0 * m * n * k * r["calls"]
+    if flops == 0.0 or ms_used <= 0:
+        return None
+    t = flops / (ms_used * 1e-3) / 1e12
+    return {"flop_per_unet_step": flops, "achieved": t, "frac": t / peak}
+
+
 def gpu_library_baseline(dev, batch: int):
     """SURVEY.md §2.1 / BASELINE.md §4.2's bar: the reference's module graph executed by the GPU LIBRARIES (cuDNN convs,
     cuBLAS linears, SDPA attention; torch eager) on the same B200 — oracle/restated.py, the restatement pinned against the
@@ -347,6 +367,7 @@ def run_b200(args):
                     "alone": {"achieved": alone, "peak": peaks["tflops_burst"], "frac": alone / peaks["tflops_burst"],
                               "ms_per_unet_step": ig["ms"], "method": "each distinct shape replayed 20x alone in a CUDA graph (burst "
                               "clocks, small problems L2-warm) vs bf16_tflops (burst)"},
+                    "executed": executed_igemm(prof, ms_used, peak),
                     "step_ms_graph": unet_step_ms,
                     "step_ms_graph_with_events": profg.get("step_ms_graph_with_events") if isinstance(profg, dict) else None}
 
