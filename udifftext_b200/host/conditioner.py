@@ -192,7 +192,8 @@ class GeneralConditioner:
         vae = lat.model._exec()
         masked = batch_c[lat.input_key].to(dev)
         mask = batch_c[resc.input_key].to(dev).float().contiguous()
-        moments = vae.encode_moments_nhwc(masked)                      # [B, h, w, 8] fp32, encoder runs once
+        # [B, h, w, 8] fp32, the encoder runs once — as one CUDA-graph launch (static output: consumed by K10 right below)
+        moments = vae.graphed("encode_moments_nhwc")(masked.float().contiguous())
         b, h, w, _ = moments.shape
         lat_shape = (b, vae.z_channels, h, w)
         noise_c = rng.randn(lat_shape, dev)                            # RNG draw #1 (c), CPU generator

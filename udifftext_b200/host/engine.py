@@ -141,8 +141,11 @@ class DiffusionEngine:
     @torch.no_grad()
     def decode_first_stage_clamped(self, z: torch.Tensor) -> torch.Tensor:
         """decode + test.py:38's clamp((x+1)/2, 0, 1) fused into the decoder's output conversion"""
-        return self.first_stage_model._exec().decode(z, in_scale=1.0 / self.scale_factor, out_scale=0.5, out_shift=0.5,
-                                                     clamp01=True)
+        vae = self.first_stage_model._exec()
+        if z.is_cuda:       # one graph launch instead of ~160 eager calls; the graph's output buffer is static -> hand out a copy
+            return vae.graphed("decode")(z.float().contiguous(), in_scale=1.0 / self.scale_factor, out_scale=0.5, out_shift=0.5,
+                                         clamp01=True).clone()
+        return vae.decode(z, in_scale=1.0 / self.scale_factor, out_scale=0.5, out_shift=0.5, clamp01=True)
 
     @torch.no_grad()
     def encode_first_stage(self, x: torch.Tensor) -> torch.Tensor:

@@ -50,6 +50,7 @@ class LabelEncoderB200:
         self.device, self.max_len, self.emb_dim, self.n_heads = dev, max_len, emb_dim, n_heads
         f = lambda k: pack.f32(sd[k]).to(dev)
         pair = lambda k: tuple(t.to(dev) for t in _pair(sd[k]))
+        self._graph = None
         self.emb = f("label_embedding.weight")
         self.pe = f("pos_embedding.pe").reshape(-1, emb_dim)[:max_len].contiguous()
         self.layers = []
@@ -68,10 +69,18 @@ class LabelEncoderB200:
         return g1[:m], g1[m:], g2
 
     def forward(self, labels: Sequence[str]) -> torch.Tensor:
-        """list[str] -> fp32 [B, max_len, emb_dim] (encoders/modules.py:1168-1173)"""
-        b = len(labels)
-        m, d = b * self.max_len, self.emb_dim
+        """list[str] -> fp32 [B, max_len, emb_dim] (encoders/modules.py:1168-1173); the 156 launches run as one CUDA graph
+        per batch size (the result is copied out of the graph's static buffer)"""
+        from .graphs import GraphCache
+        if self._graph is None:
+            self._graph = GraphCache(self.forward_idx)
         idx = label_indices(labels, self.max_len).to(self.device)
+        return self._graph(idx).clone()
+
+    def forward_idx(self, idx: torch.Tensor) -> torch.Tensor:
+        """int32 [B, max_len] character indices (device) -> fp32 [B, max_len, emb_dim]"""
+        b = idx.shape[0]
+        m, d = b * self.max_len, self.emb_dim
         f16 = lambda rows, cols: torch.empty((rows, cols), device=self.device, dtype=torch.float16)
         f32 = lambda rows, cols: torch.empty((rows, cols), device=self.device, dtype=torch.float32)
         x32, xp = f32(m, d), f16(2 * m, d)

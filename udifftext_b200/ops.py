@@ -40,6 +40,12 @@ def launch_count() -> int:
     return _launches
 
 
+def count_launches(n: int) -> None:
+    """account for kernels launched by a CUDA-graph replay (udifftext_b200.graphs)"""
+    global _launches
+    _launches += int(n)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -87,6 +87,8 @@ class VAEB200:
         self.levels = len(ch_mult)
         self._gn_ws: Optional[torch.Tensor] = None
         self._gn_ws_key = (0, 0)
+        self._graphs: dict = {}
+        self._gn_ws_old: list = []
         if build_encoder and "encoder.conv_in.weight" in sd:
             self._build_encoder(sd, dev, num_res_blocks)
         if build_decoder and "decoder.conv_in.weight" in sd:
@@ -146,6 +148,8 @@ class VAEB200:
         if self._gn_ws is None or self._gn_ws_key[0] < nb or self._gn_ws_key[1] < hw:
             nb_, hw_ = max(nb, self._gn_ws_key[0]), max(hw, self._gn_ws_key[1])
             need = max(ops.groupnorm_ws_bytes(nb_, hw_, c) for c in (64, 128, 256, 512, 1024)) // 8
+            if self._gn_ws is not None:
+                self._gn_ws_old.append(self._gn_ws)        # captured graphs may still point at the smaller workspace
             self._gn_ws = torch.empty(need, device=self.device, dtype=torch.float64)
             self._gn_ws_key = (nb_, hw_)
         return self._gn_ws
@@ -205,6 +209,16 @@ class VAEB200:
         h = self._res(self.e_mid2, h)
         a = self._gn(h, self.e_g, self.e_b, True)
         return ops.conv3x3(a, self.e_w_out, self.e_b_out, out_fp32=True)
+
+    def graphed(self, name: str):
+        """CUDA-graphed twin of `encode_moments_nhwc` / `decode` (udifftext_b200.graphs.GraphCache): same kernels, one graph
+        launch per call; returns static buffers (valid until the next call of the same shape)"""
+        from .graphs import GraphCache
+        g = self._graphs.get(name)
+        if g is None:
+            g = GraphCache(getattr(self, name))
+            self._graphs[name] = g
+        return g
 
     def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
         """reference-shaped: fp32 NCHW moments [B, 2*z, h, w] (autoencoder.py:304-309 before the posterior)"""
