@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 from udifftext_b200 import ops
 dev = torch.device("cuda", 0)
 g = torch.Generator().manual_seed(1)
-tag = "w4=" + os.environ.get("UDT_FMHA_W4", "default") + " poly=" + os.environ.get("UDT_FMHA_POLY", "default")
+tag = "ht=" + os.environ.get("UDT_FMHA_HT", "default") + " w4=" + os.environ.get("UDT_FMHA_W4", "default") + " poly=" + os.environ.get("UDT_FMHA_POLY", "default")
 for (b, n, heads, mul) in [(1, 4096, 2, 1.0), (1, 1024, 1, 6.0), (1, 2048, 1, 6.0), (2, 4096, 5, 6.0), (1, 300, 1, 6.0), (1, 192, 2, 1.0),
                            (2, 64, 20, 6.0), (3, 256, 20, 3.0), (1, 9216, 2, 4.0)]:
     c = heads * 64

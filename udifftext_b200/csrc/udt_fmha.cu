@@ -402,6 +402,288 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
 
 #ifdef UDT_TUNING
 // ------------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (tuning builds only, UDT_FMHA_HT=1) — measured on B200: correct (incl. replay-heavy and ragged cases) and 22 %
+// SLOWER than the production kernel (4096 tokens 244 -> 299 us, batch 32 1808 -> 2213 us): decoupling the two warpgroups
+// does not pay for twice the barrier round trips and tcgen05.ld / st waits per key.
+// Half-tile schedule: the score tiles are 128 queries x 64 keys and every softmax warpgroup owns THREE score buffers of
+// its own.  Why: source-level warp sampling of udt_fmha_ts_kernel shows 14 % of all samples on the `s_full` spin — in that
+// kernel the three 128-column score buffers rotate between the two warpgroups, S(c+3) can only be issued after P(c) V (P(c)
+// lives in the buffer S(c+3) overwrites), and c / c+3 belong to DIFFERENT warpgroups, so each warpgroup's next scores wait
+// for the other one's progress.  Tensor memory is full (384 score + 128 output columns), a fourth 128-column buffer does not
+// fit — but six 64-column buffers do: warpgroup t owns columns [t*192, t*192+192) as buffers b = 0..2, the scores of its
+// half-tile hc+3 reuse the buffer of ITS OWN half-tile hc, and the MMA warp serves whichever warpgroup has its probabilities
+// ready (non-blocking test of both p_full barriers).  The two warpgroups only share the K / V ring and the tensor pipe.
+// Same thread-per-row softmax as above (exp2 domain, lazy rescale, single pass with replay), 64 keys per step.
+constexpr int kHBufs = 3;
+
+__global__ void __launch_bounds__(kThreads, 1) udt_fmha_h_kernel(const __grid_constant__ FmhaParams p) {
+  griddep_launch();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base = smem_raw + (base_addr - raw_addr);
+
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(base + kOffCtrl);
+  uint64_t* kv_full = q_full + 1;                  // [kKvStages]
+  uint64_t* kv_empty = kv_full + kKvStages;        // [kKvStages]  one arrival per warpgroup (its P V of the tile's second half)
+  uint64_t* s_full = kv_empty + kKvStages;         // [2][kHBufs]
+  uint64_t* p_full = s_full + 2 * kHBufs;          // [2]
+  uint64_t* o_full = p_full + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int b, h, q0, ntiles;
+  if (!fmha_work(p, b, h, q0, ntiles)) return;
+  const int nkv = (p.Nkv + kTile - 1) / kTile;
+  const int H = 2 * nkv;                           // half-tiles per warpgroup
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], static_cast<uint32_t>(ntiles));
+    }
+    for (int i = 0; i < 2 * kHBufs; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int col = h * kD;
+      mbar_expect_tx(q_full, static_cast<uint32_t>(ntiles * kTileBytes));
+      for (int t = 0; t < ntiles; ++t)
+        tma_load_2d(&p.mapQ, q_full, base + kOffQ + t * kTileBytes, col, b * p.Nq + q0 + t * kTile);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1u);
+        mbar_expect_tx(&kv_full[s], 2u * kTileBytes);
+        tma_load_2d(&p.mapK, &kv_full[s], base + kTsOffK + s * kTileBytes, col, b * p.Nkv + j * kTile);
+        tma_load_2d(&p.mapV, &kv_full[s], base + kTsOffV + s * kTileBytes, col, b * p.Nkv + j * kTile);
+        if (++s == kKvStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const bool issuer = elect_one();
+    const uint32_t idesc_s = umma_idesc_f16(128, 64, false, false);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
+    int kv_seen = -1;                              // highest key tile whose K / V are known to have landed
+    int hs[2] = {0, 0}, hp[2] = {0, 0};            // next half-tile whose scores / whose P V is to be issued, per warpgroup
+    // S(t, hs[t]) = Q_t K_j[half]^T -> buffer hs[t] % 3 of warpgroup t, if that buffer is free (its previous P V has been
+    // issued) and key tile j has landed.  Never blocks: a warpgroup that runs ahead of the K / V ring must not keep the MMA
+    // warp from serving the other one (whose progress frees the ring stage it is waiting for).
+    auto try_issue_s = [&](int t) -> bool {
+      if (hs[t] >= H || hs[t] >= hp[t] + kHBufs) return false;
+      const int hc = hs[t], j = hc >> 1, half = hc & 1, bf = hc % kHBufs;
+      while (kv_seen < j) {
+        const int nx = kv_seen + 1;
+        if (!__all_sync(0xffffffffu, mbar_test_wait(&kv_full[nx % kKvStages], static_cast<uint32_t>((nx / kKvStages) & 1))))
+          return false;
+        kv_seen = nx;
+      }
+      tc_fence_after();
+      if (issuer) {
+        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + t * kTileBytes);
+        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kTsOffK + (j % kKvStages) * kTileBytes + half * (64 * 128));
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk)
+          umma_f16_ss(tmem_base + t * 192 + bf * 64, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
+                      idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit(&s_full[t * kHBufs + bf]);
+      }
+      __syncwarp();
+      ++hs[t];
+      return true;
+    };
+    mbar_wait(q_full, 0);
+    int remaining = ntiles * H;
+    uint32_t spins = 0;
+    while (remaining > 0) {
+      bool progressed = false;
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (t < ntiles && try_issue_s(t)) progressed = true;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t >= ntiles || hp[t] >= H) continue;
+        const bool ready = __all_sync(0xffffffffu, mbar_test_wait(&p_full[t], static_cast<uint32_t>(hp[t] & 1)));
+        if (!ready) continue;
+        const int hc = hp[t], j = hc >> 1, half = hc & 1, bf = hc % kHBufs;
+        tc_fence_after();
+        if (issuer) {
+          const uint32_t v_addr = base_addr + kTsOffV + (j % kKvStages) * kTileBytes;
+          const uint32_t p_tmem = tmem_base + t * 192 + bf * 64;   // P (fp16 pairs) over the first 32 columns of its score buffer
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + (half * 4 + kk) * 16 * 128, 8192);
+            umma_f16_ts(tmem_base + kColO + t * 64, p_tmem + kk * 8, dv, idesc_o, (hc | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[t]);
+          if (half == 1) umma_commit(&kv_empty[j % kKvStages]);   // this warpgroup is done with key tile j
+        }
+        __syncwarp();
+        ++hp[t];
+        --remaining;
+        progressed = true;
+      }
+      if (progressed) spins = 0;
+      else if (++spins > UDT_SPIN_LIMIT) asm volatile("trap;");
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups (thread = query row)
+    const int t = warp >> 2;
+    if (t < ntiles) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t o_addr = tmem_base + lane_base + kColO + t * 64;
+      const float sl2 = p.scale_log2;
+      float m_ref = -INFINITY, l = 0.0f;
+
+      auto rescale = [&](bool need, float m_tile, int hc) {
+        const float m_new = need ? m_tile : m_ref;
+        const float alpha = need ? ex2_approx(m_ref - m_new) : 1.0f;
+        l *= alpha;
+        if (hc > 0) {
+          mbar_wait(&o_full[t], static_cast<uint32_t>((hc - 1) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(o_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(o_addr + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+        m_ref = m_new;
+      };
+
+      int bf = 0, use = 0;     // bf = hc % 3, use = hc / 3
+      for (int hc = 0; hc < H; ++hc) {
+        mbar_wait(&s_full[t * kHBufs + bf], static_cast<uint32_t>(use & 1));
+        tc_fence_after();
+        const uint32_t s_addr = tmem_base + lane_base + t * 192 + bf * 64;
+        const int key_lim = p.Nkv - (hc >> 1) * kTile - (hc & 1) * 64;   // my keys >= key_lim are padding (last tile only)
+        const bool partial = key_lim < 64;
+        float rowsum = 0.0f;
+        bool replay = (hc == 0) || partial;
+        uint32_t pall[32];
+        if (!replay) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(s_addr, va);
+          tmem_ld_wait_dep(va);
+          tmem_ld32(s_addr + 32, vb);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(va[i]), sl2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(va[i + 1]), sl2, -m_ref));
+            rowsum += p0 + p1;
+            pall[i >> 1] = pack_half2(p0, p1);
+          }
+          tmem_ld_wait_dep(vb);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[i]), sl2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[i + 1]), sl2, -m_ref));
+            rowsum += p0 + p1;
+            pall[16 + (i >> 1)] = pack_half2(p0, p1);
+          }
+          replay = __any_sync(0xffffffffu, !(rowsum <= 256.0f));   // stale reference (or inf / nan): two-pass path
+        }
+        if (replay) {
+          uint32_t v[32];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!partial || ch * 32 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          const float m_tile = mx * sl2;
+          const bool need = m_tile > m_ref + kLazyThreshold;
+          if (__any_sync(0xffffffffu, need)) rescale(need, m_tile, hc);
+          rowsum = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            tmem_ld32(s_addr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
+              if (partial) {
+                const int k0 = ch * 32 + i;
+                if (k0 >= key_lim) p0 = 0.0f;
+                if (k0 + 1 >= key_lim) p1 = 0.0f;
+              }
+              rowsum += p0 + p1;
+              pall[ch * 16 + (i >> 1)] = pack_half2(p0, p1);
+            }
+          }
+        }
+        l += rowsum;
+        tmem_st32(s_addr, pall);                 // P over the first 32 columns of my own (consumed) score buffer
+        tmem_st_wait();
+        if (hc > 0) mbar_wait(&o_full[t], static_cast<uint32_t>((hc - 1) & 1));   // observe every o_full phase
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        if (++bf == kHBufs) { bf = 0; ++use; }
+      }
+      mbar_wait(&o_full[t], static_cast<uint32_t>((H - 1) & 1));
+      tc_fence_after();
+      const int qrow = q0 + t * kTile + row;
+      const float inv = 1.0f / l;
+      uint4* o4 = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.Nq + min(qrow, p.Nq - 1)) * p.ldo + h * kD);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(o_addr + c * 32, v);
+        tmem_ld_wait();
+        if (qrow < p.Nq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 ov;
+            ov.x = pack_half2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+            ov.y = pack_half2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+            ov.z = pack_half2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+            ov.w = pack_half2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+            o4[c * 4 + g] = ov;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // EXPERIMENT (tuning builds only, UDT_FMHA_W4=1) — measured on B200: correct (same errors to 4 digits incl. replay and ragged
 // tiles) and 7 % SLOWER than the two-warpgroup kernel (4096 tokens 244 -> 260 us, 1024 tokens 45.2 -> 49.1 us): the kernel is
 // not limited by the number of warps a scheduler can pick from.
@@ -728,6 +1010,20 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
   dim3 grid(static_cast<unsigned>(p.pairs_full + 2 * (npairs - p.pairs_full)), 1, 1);
   // tuning builds: UDT_FMHA_POLY=4 moves every 4th exponential from MUFU to the FMA pipe.  Measured on B200: no gain
   // (4096 tokens 249.0 -> 250.4 us; every 2nd: 275 us) — the kernel is bound by the TMEM read path as much as by MUFU
+#ifdef UDT_TUNING
+  // experiment: half-tile schedule (every softmax warpgroup owns three 64-key score buffers), UDT_FMHA_HT=1 — 22 % slower
+  static const int use_ht = tune_int("UDT_FMHA_HT", 0);
+  if (use_ht) {
+    static bool ht_attr = false;
+    if (!ht_attr) {
+      cudaError_t e = cudaFuncSetAttribute(udt_fmha_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
+      if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha ht smem): %s", cudaGetErrorString(e));
+      ht_attr = true;
+    }
+    udt_host::launch_pdl(udt_fmha_h_kernel, dim3(grid), dim3(kThreads), kTsSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
+    return check_launch("udt_fmha_fwd (half tiles)");
+  }
+#endif
 #ifdef UDT_TUNING
   // experiment: four softmax warpgroups (two per score tile), UDT_FMHA_W4=1 — measured 7 % slower, see the kernel's header
   static const int use_w4 = tune_int("UDT_FMHA_W4", 0);
