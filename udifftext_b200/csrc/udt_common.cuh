@@ -88,6 +88,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait with a hardware suspend-time hint: the warp stays descheduled inside try_wait until the phase completes (wake-up is
+// driven by the barrier, no polling latency) or `hint_ns` elapse, so a role warp that mostly waits does not take issue
+// slots from the compute warps of its sub-partition.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 2000) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (ok) break;
+    if (++spins > UDT_SPIN_LIMIT) {
+      asm volatile("trap;");
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // thread-block clusters (CTA pairs for tcgen05 cta_group::2, DSMEM exchange) and programmatic dependent launch
 // ----------------------------------------------------------------------------------------------

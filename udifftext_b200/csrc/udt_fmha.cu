@@ -42,8 +42,18 @@ constexpr float kLazyThreshold = 8.0f;  // log2 units
 
 #ifdef UDT_IGEMM_TRACE
 #define UDT_FDBG(bit) (p.debug & (bit))    // tuning builds (UDT_TRACE=1): UDT_FMHA_DEBUG experiment switches
+// UDT_FMHA_DEBUG & 64: lane 0 of every softmax warp of CTA 0 stamps clock() at fixed points of key tiles 8..11 and prints them
+// when the CTA ends (scripts/fmha_timeline.py).  (Stamps in the MMA-issuing warps lengthen the issue chain they measure.)
+#define UDT_FSTAMP_DECL uint32_t stamps[4 * 8]; const bool stamp_cta = (p.debug & 64) && blockIdx.x == 0 && lane == 0
+#define UDT_FSTAMP(j, slot) do { if (stamp_cta && (j) >= 8 && (j) < 12) stamps[((j) - 8) * 8 + (slot)] = static_cast<uint32_t>(clock()); } while (0)
+#define UDT_FSTAMP_DUMP(nj) do { if (stamp_cta && (nj) >= 12) for (int jj = 0; jj < 4; ++jj) \
+  printf("FSTAMP w%d j%d %u %u %u %u %u %u %u %u\n", warp, jj + 8, stamps[jj * 8], stamps[jj * 8 + 1], stamps[jj * 8 + 2], \
+         stamps[jj * 8 + 3], stamps[jj * 8 + 4], stamps[jj * 8 + 5], stamps[jj * 8 + 6], stamps[jj * 8 + 7]); } while (0)
 #else
 #define UDT_FDBG(bit) (false)
+#define UDT_FSTAMP_DECL
+#define UDT_FSTAMP(j, slot)
+#define UDT_FSTAMP_DUMP(nj)
 #endif
 
 struct FmhaParams {
@@ -122,12 +132,11 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
 
   uint64_t* q_full = reinterpret_cast<uint64_t*>(base + kOffCtrl);
   uint64_t* kv_full = q_full + 1;            // [kTsKvStages]
-  uint64_t* kv_empty = kv_full + kTsKvStages;  // [kTsKvStages]
-  uint64_t* s_full = kv_empty + kTsKvStages;   // [kSBufs]  scores of a computation are in TMEM
-  uint64_t* s_free = s_full + kSBufs;        // [kSBufs]  the consuming warpgroup has read them
-  uint64_t* p_full = s_free + kSBufs;        // [2]       P_t(j) is in shared memory
-  uint64_t* o_full = p_full + 2;             // [2]       P_t(j) V_j has been accumulated into O_t
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = kv_full + kTsKvStages;  // [kSBufs]  scores of a computation are in TMEM
+  uint64_t* p_full = s_full + kSBufs;        // [2]       P_t(j) is in TMEM (over its score buffer)
+  uint64_t* o_full = p_full + 2;             // [2]       P_t(j) V_j has been accumulated into O_t (softmax warpgroup t waits)
+  uint64_t* pv_done = o_full + 2;            // [kSBufs]  same event per score buffer (the score issuer waits: buffer / K,V stage free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + kSBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,13 +150,10 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
     tma_prefetch_desc(&p.mapK);
     tma_prefetch_desc(&p.mapV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < kTsKvStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
+    for (int i = 0; i < kTsKvStages; ++i) mbar_init(&kv_full[i], 1);
     for (int i = 0; i < kSBufs; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 128);
+      mbar_init(&pv_done[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&p_full[i], 128);
@@ -163,74 +169,84 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
   griddep_wait();     // PDL: q / k / v are produced by the previous kernel
 
   if (warp == 9) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const int col = h * kD;
+    // ------------------------------------------------------------------ score issuer + TMA producer
+    // S(c) = Q_t K_j^T goes into score buffer c % 3 once P(c-3) V — the previous user of that buffer, issued by warp 8 — has
+    // COMPLETED (pv_done; the two issuing threads are ordered through that barrier, tcgen05.commit -> wait ->
+    // tcgen05.fence::after_thread_sync).  The same event frees the K / V stage of a finished key tile, so this warp also
+    // refills the ring: no producer warp, no kv_empty barriers, no commit for them.
+    // Why two issuing warps: one thread issuing all twelve MMAs + three commits of a computation needs ~900 clk per
+    // computation (~40 clk per tcgen05.mma, ~100 per commit; scripts/fmha_timeline.py), ~2000 clk per key tile against
+    // ~1750 clk of softmax work per warpgroup — the issue chain, not the exp pipe, set the pace; and while a tcgen05.mma waits
+    // for room in the tensor-pipe queue it sits at the head of its sub-partition's MIO queue, where the MUFU / tcgen05.ld
+    // instructions of that sub-partition's two softmax warps wait behind it (they needed ~2450 clk per key tile and moved
+    // with the issuing warp when it was placed on another sub-partition).  Split, each thread has at most 2/3 of that work,
+    // the chains overlap, and the MIO cost is shared by two sub-partitions.
+    const bool issuer = elect_one();
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+    const int col = h * kD;
+    auto load_kv = [&](int j, int stage) {
+      mbar_expect_tx(&kv_full[stage], 2u * kTileBytes);
+      tma_load_2d(&p.mapK, &kv_full[stage], base + kTsOffK + stage * kTileBytes, col, b * p.Nkv + j * kTile);
+      tma_load_2d(&p.mapV, &kv_full[stage], base + kTsOffV + stage * kTileBytes, col, b * p.Nkv + j * kTile);
+    };
+    if (issuer) {
       mbar_expect_tx(q_full, static_cast<uint32_t>(ntiles * kTileBytes));
       for (int t = 0; t < ntiles; ++t)
         tma_load_2d(&p.mapQ, q_full, base + kOffQ + t * kTileBytes, col, b * p.Nq + q0 + t * kTile);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1u);
-        mbar_expect_tx(&kv_full[s], 2u * kTileBytes);
-        tma_load_2d(&p.mapK, &kv_full[s], base + kTsOffK + s * kTileBytes, col, b * p.Nkv + j * kTile);
-        tma_load_2d(&p.mapV, &kv_full[s], base + kTsOffV + s * kTileBytes, col, b * p.Nkv + j * kTile);
-        if (++s == kTsKvStages) { s = 0; ph ^= 1u; }
-      }
+      for (int j = 0; j < kTsKvStages && j < nkv; ++j) load_kv(j, j);
     }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
-    const bool issuer = elect_one();
-    const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
-    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
-    auto issue_s = [&](const CompCursor& k) {
-      if (k.t == 0) mbar_wait(&kv_full[k.stage], static_cast<uint32_t>(k.kvphase));
-      // (buffer reuse needs no barrier: P of computation c lives in S buffer c % 3, and S(c+3) is issued after P V(c) by this
-      //  same thread — the tensor pipe executes them in order)
+    __syncwarp();
+    mbar_wait(q_full, 0);
+    CompCursor ks, kd;   // kd trails ks by kSBufs computations: the previous user of the score buffer ks is about to overwrite
+    ks.init();
+    kd.init();
+    for (; ks.c < ncomp; ks.advance(ntiles, kTsKvStages)) {
+      if (ks.c >= kSBufs) {
+        mbar_wait(&pv_done[kd.b], static_cast<uint32_t>(kd.u & 1));
+        if (kd.t == ntiles - 1 && kd.j + kTsKvStages < nkv && issuer)   // key tile kd.j is finished: its stage takes tile j + stages
+          load_kv(kd.j + kTsKvStages, kd.stage);
+        kd.advance(ntiles, kTsKvStages);
+      }
+      if (ks.t == 0) mbar_wait(&kv_full[ks.stage], static_cast<uint32_t>(ks.kvphase));
       tc_fence_after();
       if (issuer) {
-        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + k.t * kTileBytes);
-        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kTsOffK + k.stage * kTileBytes);
+        const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + ks.t * kTileBytes);
+        const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kTsOffK + ks.stage * kTileBytes);
 #pragma unroll
         for (int kk = 0; kk < kD / 16; ++kk)
-          umma_f16_ss(tmem_base + kColS + k.b * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
+          umma_f16_ss(tmem_base + kColS + ks.b * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
                       idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(&s_full[k.b]);
+        umma_commit(&s_full[ks.b]);
       }
       __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    CompCursor ks, kp;   // score cursor runs kSBufs computations ahead of the PV cursor
-    ks.init();
-    kp.init();
-    for (int i = 0; i < kSBufs && ks.c < ncomp; ++i) {
-      issue_s(ks);
-      ks.advance(ntiles, kTsKvStages);
     }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ PV issuer (converged warp, one elected lane issues)
+    const bool issuer = elect_one();
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
+    CompCursor kp;
+    kp.init();
     for (; kp.c < ncomp; kp.advance(ntiles, kTsKvStages)) {
-      mbar_wait(&p_full[kp.t], static_cast<uint32_t>(kp.j & 1));   // P_t(j) is in smem, S of this computation is released
+      mbar_wait(&p_full[kp.t], static_cast<uint32_t>(kp.j & 1));   // P_t(j) is in TMEM over the first 64 columns of its score buffer
+      if (kp.t == 0) mbar_wait(&kv_full[kp.stage], static_cast<uint32_t>(kp.kvphase));   // V_j (lands with K_j; cannot be refilled before this PV)
       tc_fence_after();
       if (issuer) {
         const uint32_t v_addr = base_addr + kTsOffV + kp.stage * kTileBytes;
-        const uint32_t p_tmem = tmem_base + kColS + kp.b * 128;   // P (fp16 pairs) aliases the first 64 columns of its S buffer
+        const uint32_t p_tmem = tmem_base + kColS + kp.b * 128;
 #pragma unroll
         for (int kk = 0; kk < kTile / 16; ++kk) {
           const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
           umma_f16_ts(tmem_base + kColO + kp.t * 64, p_tmem + kk * 8, dv, idesc_o, (kp.j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&o_full[kp.t]);
-        if (kp.t == ntiles - 1) umma_commit(&kv_empty[kp.stage]);   // last reader of this K/V stage
+        umma_commit(&pv_done[kp.b]);
       }
       __syncwarp();
-      if (ks.c < ncomp) {
-        issue_s(ks);
-        ks.advance(ntiles, kTsKvStages);
-      }
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
     const int t = warp >> 2;  // query tile handled by this warpgroup
+    UDT_FSTAMP_DECL;
     if (t < ntiles) {
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;
@@ -263,8 +279,10 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
       };
 
       for (int j = 0; j < nkv; ++j) {
+        UDT_FSTAMP(j, 0);
         mbar_wait(&s_full[sb], static_cast<uint32_t>(su & 1));
         tc_fence_after();
+        UDT_FSTAMP(j, 1);
         const uint32_t s_addr = tmem_base + lane_base + kColS + sb * 128;
         const int key_lim = p.Nkv - j * kTile;  // keys >= key_lim of this tile are padding (only on the last tile)
         const bool partial = key_lim < kTile;
@@ -300,8 +318,10 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
           };
           tmem_ld32(s_addr, va);
           tmem_ld_wait_dep(va);
+          UDT_FSTAMP(j, 2);
           tmem_ld32(s_addr + 32, vb);      // the next 32 columns fly during the math
           exp_chunk(va, 0);
+          UDT_FSTAMP(j, 3);
           tmem_ld_wait_dep(vb);
           tmem_ld32(s_addr + 64, va);
           exp_chunk(vb, 1);
@@ -309,7 +329,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
           tmem_ld32(s_addr + 96, vb);
           exp_chunk(va, 2);
           tmem_ld_wait_dep(vb);
+          UDT_FSTAMP(j, 4);
           exp_chunk(vb, 3);
+          UDT_FSTAMP(j, 5);
           replay = __any_sync(0xffffffffu, !(rowsum <= 256.0f)) && !UDT_FDBG(3);   // also catches inf / nan
         }
         if (replay) {
@@ -357,11 +379,13 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
           tmem_st32(s_addr + 32, hi);
           tmem_st_wait();
         }
+        UDT_FSTAMP(j, 6);
         // observe every o_full phase (the wait is almost always already satisfied: P_t V_{j-1} ran during this tile's
         // exponentials); a parity wait that skipped phases would be ambiguous in rescale() and at the end
         if (j > 0) mbar_wait(&o_full[t], static_cast<uint32_t>((j - 1) & 1));
         tc_fence_before();         // TMEM reads of S / writes of P, O_t ordered before the arrive
         mbar_arrive(&p_full[t]);
+        UDT_FSTAMP(j, 7);
         sb += ntiles;
         if (sb >= kSBufs) { sb -= kSBufs; ++su; }
       }
@@ -387,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
           }
         }
       }
+      UDT_FSTAMP_DUMP(nkv);
     }
   }
 
