@@ -1,8 +1,8 @@
-"""Per-tile timeline of the FMHA kernel's softmax warps and MMA warp (tuning build, UDT_FMHA_DEBUG=64): CTA 0 prints clock()
-stamps of key tiles 8..11; this script runs one launch and prints the stamps as deltas.
+"""Per-tile timeline of the FMHA kernel's softmax warps (build with `UDT_TRACE=1 UDT_STAMPS=1 python -m udifftext_b200.build
+--force`): CTA 0 prints clock() stamps of key tiles 8..11; this script runs one launch and prints the stamps as deltas.
 softmax slots: 0 before s_full wait, 1 scores ready, 2 first 32 columns in registers, 3 chunk 0 done, 4 last chunk loaded,
-5 exponentials done, 6 P stored (tcgen05.st complete), 7 p_full arrived.  MMA warp (w8), per query tile t: 4t+0 before p_full
-wait, 4t+1 P ready, 4t+2 PV issued, 4t+3 next S issued."""
+5 exponentials done, 6 P stored (tcgen05.st complete), 7 p_full arrived.  (Stamps inside the MMA-issuing warps were used once
+to find the issue chain — ~40 clk per tcgen05.mma, ~100 per commit — and removed: they lengthen the chain they measure.)"""
 import os, subprocess, sys
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import torch
@@ -24,7 +24,7 @@ for line in out.splitlines():
         f = line.split()
         rows[(int(f[1][1:]), int(f[2][1:]))] = [int(x) for x in f[3:]]
 if not rows:
-    print("no stamps (production build?)"); sys.exit(1)
+    print("no stamps (build with UDT_TRACE=1 UDT_STAMPS=1)"); sys.exit(1)
 t0 = min(v[0] for v in rows.values())
 for (w, j), v in sorted(rows.items()):
     rel = [(x - t0) & 0xffffffff for x in v]

@@ -38,7 +38,8 @@ def _flags() -> list:
     switch (UDT_* environment variables, udt_host.h tune_int) are compiled in.  A production build contains neither: it
     reads no environment variable and keeps debug code out of the hot loops."""
     tuning = os.environ.get("UDT_TRACE", "0") not in ("", "0")
-    return NVCC_FLAGS + (["-DUDT_IGEMM_TRACE", "-DUDT_TUNING"] if tuning else [])
+    stamps = os.environ.get("UDT_STAMPS", "0") not in ("", "0")   # per-tile clock stamps in the FMHA kernel (scripts/fmha_timeline.py)
+    return NVCC_FLAGS + (["-DUDT_IGEMM_TRACE", "-DUDT_TUNING"] if tuning else []) + (["-DUDT_FMHA_STAMPS"] if tuning and stamps else [])
 
 
 def _source_digest() -> str:

@@ -42,15 +42,19 @@ constexpr float kLazyThreshold = 8.0f;  // log2 units
 
 #ifdef UDT_IGEMM_TRACE
 #define UDT_FDBG(bit) (p.debug & (bit))    // tuning builds (UDT_TRACE=1): UDT_FMHA_DEBUG experiment switches
-// UDT_FMHA_DEBUG & 64: lane 0 of every softmax warp of CTA 0 stamps clock() at fixed points of key tiles 8..11 and prints them
-// when the CTA ends (scripts/fmha_timeline.py).  (Stamps in the MMA-issuing warps lengthen the issue chain they measure.)
+#else
+#define UDT_FDBG(bit) (false)
+#endif
+#ifdef UDT_FMHA_STAMPS
+// tuning builds with UDT_STAMPS=1, UDT_FMHA_DEBUG & 64: lane 0 of every softmax warp of CTA 0 stamps clock() at fixed points of
+// key tiles 8..11 and prints them when the CTA ends (scripts/fmha_timeline.py).  The stamps cost registers (spills) — timings of
+// such a build are not comparable; stamps in the MMA-issuing warps would lengthen the issue chain they measure.
 #define UDT_FSTAMP_DECL uint32_t stamps[4 * 8]; const bool stamp_cta = (p.debug & 64) && blockIdx.x == 0 && lane == 0
 #define UDT_FSTAMP(j, slot) do { if (stamp_cta && (j) >= 8 && (j) < 12) stamps[((j) - 8) * 8 + (slot)] = static_cast<uint32_t>(clock()); } while (0)
 #define UDT_FSTAMP_DUMP(nj) do { if (stamp_cta && (nj) >= 12) for (int jj = 0; jj < 4; ++jj) \
   printf("FSTAMP w%d j%d %u %u %u %u %u %u %u %u\n", warp, jj + 8, stamps[jj * 8], stamps[jj * 8 + 1], stamps[jj * 8 + 2], \
          stamps[jj * 8 + 3], stamps[jj * 8 + 4], stamps[jj * 8 + 5], stamps[jj * 8 + 6], stamps[jj * 8 + 7]); } while (0)
 #else
-#define UDT_FDBG(bit) (false)
 #define UDT_FSTAMP_DECL
 #define UDT_FSTAMP(j, slot)
 #define UDT_FSTAMP_DUMP(nj)
