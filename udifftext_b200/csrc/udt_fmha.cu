@@ -205,13 +205,13 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
     ks.init();
     kd.init();
     for (; ks.c < ncomp; ks.advance(ntiles, kTsKvStages)) {
+      if (ks.t == 0) mbar_wait(&kv_full[ks.stage], static_cast<uint32_t>(ks.kvphase));   // K_j: long landed, checked off the critical path
       if (ks.c >= kSBufs) {
         mbar_wait(&pv_done[kd.b], static_cast<uint32_t>(kd.u & 1));
         if (kd.t == ntiles - 1 && kd.j + kTsKvStages < nkv && issuer)   // key tile kd.j is finished: its stage takes tile j + stages
           load_kv(kd.j + kTsKvStages, kd.stage);
         kd.advance(ntiles, kTsKvStages);
       }
-      if (ks.t == 0) mbar_wait(&kv_full[ks.stage], static_cast<uint32_t>(ks.kvphase));
       tc_fence_after();
       if (issuer) {
         const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kOffQ + ks.t * kTileBytes);
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
           const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
           umma_f16_ts(tmem_base + kColO + kp.t * 64, p_tmem + kk * 8, dv, idesc_o, (kp.j | kk) != 0 ? 1u : 0u);
         }
+        umma_commit(&pv_done[kp.b]);   // first: the score issuer's wait is on the critical path, the warpgroup's is not
         umma_commit(&o_full[kp.t]);
-        umma_commit(&pv_done[kp.b]);
       }
       __syncwarp();
     }
