@@ -35,7 +35,7 @@ def main():
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for _ in range(5):
-        r.graph.replay()
+        r.replay()
     g1.record()
     torch.cuda.synchronize()
     print(json.dumps({"config": f"batch {b}, {px}x{px}, {steps} steps (BASELINE configs[4])", "images_per_s": b / ms * 1e3,

@@ -28,7 +28,7 @@ with torch.no_grad():
         t3 = sync()
         t4h = time.perf_counter()
         for i in range(num_sigmas - 1):
-            runner.graph.replay()
+            runner.replay()
         t4e = time.perf_counter()
         t4 = sync()
         print(f"prepare {1e3*(t1-t0):.2f} ms | begin {1e3*(t2-t1):.2f} | 50 steps {1e3*(t3-t2):.2f} | 50 bare replays {1e3*(t4-t3):.2f} (host enqueue {1e3*(t4e-t4h):.2f})")

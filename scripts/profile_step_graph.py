@@ -89,7 +89,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        r.graph.replay()
+        r.replay()
     e1.record()
     torch.cuda.synchronize()
     print(f"whole-step graph replay: {e0.elapsed_time(e1) / 5:.3f} ms  ({r.launches_per_step} C-ABI calls)")

@@ -36,8 +36,9 @@ def main():
     bad = 0
     for i in range(n):
         r.x.copy_(x0)
-        r.row.copy_(r.table[i % 3: i % 3 + 1])
-        r.graph.replay()
+        r._next = -1
+        r.set_step(i % 3)          # the captured step loads its row through the device-side step counter
+        r.replay()
         if i % 3 == 0:
             torch.cuda.synchronize()
             if ref_eps is None:

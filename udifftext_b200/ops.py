@@ -139,12 +139,12 @@ def profile_step(runner, warm: int = 2, reps: int = 20) -> dict:
     step_ms_graph = None
     if runner.graph is not None:
         for _ in range(warm):
-            runner.graph.replay()
+            runner.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(5):
-            runner.graph.replay()
+            runner.replay()
         e1.record()
         torch.cuda.synchronize()
         step_ms_graph = e0.elapsed_time(e1) / 5
