@@ -1,12 +1,17 @@
 // udt_fmha.cu — K4: softmax(Q K^T * scale) V for head dim 64 on tcgen05 tensor cores (sm_100a).
 //
 // One CTA owns two 128-row query tiles of one (batch, head) and streams the keys/values in 128-row tiles:
-//   warp 9      TMA producer : Q tiles once, then a 4-stage ring of K / V tiles (128B-swizzled boxes)
-//   warp 8      MMA issuer   : S = Q_t K_j^T     (M128 N128 K64, K-major operands)       -> one of THREE S buffers in TMEM
-//                              O_t += P_t V_j    (M128 N64 K128, P from TMEM, V MN-major) -> TMEM O_t (accumulating)
+//   warp 8      PV issuer    : O_t += P_t V_j    (M128 N64 K128, P from TMEM, V MN-major) -> TMEM O_t (accumulating);
+//                              commits per score buffer (pv_done) and per query tile (o_full)
+//   warp 9      score issuer : S = Q_t K_j^T     (M128 N128 K64, K-major operands)       -> one of THREE S buffers in TMEM,
+//                + TMA ring    issued once the PV that last used the buffer has COMPLETED; the same event frees the K / V stage
+//                              of a finished key tile, so this warp also loads Q once and keeps the 4-stage K / V ring full
+//                              (128B-swizzled boxes).  Two issuing warps because ONE thread issuing the 12 MMAs + 3 commits of
+//                              a computation was the kernel's pace-setter (see the comment in the kernel and DESIGN.md 4.1).
 //                              The score tiles of both query tiles rotate through three TMEM buffers, so the scores a
-//                              softmax warpgroup needs next are computed while it still works on its current tile
-//                              (with one buffer per query tile the exp pipe idled during every S MMA).
+//                              softmax warpgroup needs next are computed while it still works on its current tile, and the
+//                              rotation keeps the two warpgroups in anti-phase on the exp pipe (a private score buffer per
+//                              warpgroup ran them in lockstep: 270 vs 228 us).
 //   warps 0-3 / 4-7          : softmax warpgroup of tile 0 / tile 1; thread = query row.  Online softmax in fp32
 //                              (exp2 domain) with LAZY rescaling: the running output stays in TMEM and is only
 //                              rescaled (tcgen05.ld / st round trip) when the row maximum grows by more than 2^8
