@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 from udifftext_b200 import ops
 dev = torch.device("cuda", 0)
 g = torch.Generator().manual_seed(1)
-tag = "pace=" + os.environ.get("UDT_FMHA_PACE_S", "-") + "/" + os.environ.get("UDT_FMHA_PACE_PV", "-") + " dbg=" + os.environ.get("UDT_FMHA_DEBUG", "0") + " ht=" + os.environ.get("UDT_FMHA_HT", "default") + " w4=" + os.environ.get("UDT_FMHA_W4", "default") + " poly=" + os.environ.get("UDT_FMHA_POLY", "default")
+tag = "persist=" + os.environ.get("UDT_FMHA_PERSIST", "0") + " pace=" + os.environ.get("UDT_FMHA_PACE_S", "-") + "/" + os.environ.get("UDT_FMHA_PACE_PV", "-") + " dbg=" + os.environ.get("UDT_FMHA_DEBUG", "0") + " ht=" + os.environ.get("UDT_FMHA_HT", "default") + " w4=" + os.environ.get("UDT_FMHA_W4", "default") + " poly=" + os.environ.get("UDT_FMHA_POLY", "default")
 ACC = [] if os.environ.get("UDT_FMHA_SKIP_ACC") else [(1, 4096, 2, 1.0), (1, 1024, 1, 6.0), (1, 2048, 1, 6.0), (2, 4096, 5, 6.0), (1, 300, 1, 6.0), (1, 192, 2, 1.0),
                            (2, 64, 20, 6.0), (3, 256, 20, 3.0), (1, 9216, 2, 4.0)]
 for (b, n, heads, mul) in ACC:

@@ -64,6 +64,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// invalidate an mbarrier so that its memory can be initialised again (persistent kernels re-arm their barriers per epoch)
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // non-blocking phase test (no hardware suspend): for polling several barriers in turn
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -73,6 +73,7 @@ struct FmhaParams {
   int32_t debug;   // UDT_FMHA_DEBUG experiment switches (tuning only; 0 in production)
   int32_t pairs_per_bh;   // CTAs [0, pairs_full) own a PAIR of query tiles (256 rows) of one (batch, head), numbered
   int32_t pairs_full;     // (b * heads + h) * pairs_per_bh + pair; the CTAs after them own ONE tile of the remaining pairs
+  int32_t num_items;      // pairs_full + single-tile items (= the grid of the one-item-per-CTA kernel)
 };
 
 // 2^x on the FMA / ALU pipes (the MUFU pipe, 16 ex2/clk/SM, is the busiest pipe of this kernel: 66 % under ncu): round-to-
@@ -90,8 +91,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 // Work of this CTA.  The grid is linear: whole waves of tile pairs first, then — when the last, partial wave would leave
 // more than half of the SMs idle — its pairs as twice as many single-tile CTAs (a single-tile CTA has the exp pipe and
 // the TMEM read port to itself and finishes in ~0.55 of a pair's time, so the tail wave shrinks accordingly).
-__device__ __forceinline__ bool fmha_work(const FmhaParams& p, int& b, int& h, int& q0, int& ntiles) {
-  const int L = static_cast<int>(blockIdx.x);
+__device__ __forceinline__ bool fmha_item(const FmhaParams& p, int L, int& b, int& h, int& q0, int& ntiles) {
   int pair = L, half = 0;
   const bool single = L >= p.pairs_full;
   if (single) {
@@ -105,6 +105,10 @@ __device__ __forceinline__ bool fmha_work(const FmhaParams& p, int& b, int& h, i
   q0 = (pair - bh * p.pairs_per_bh) * 2 * kTile + half * kTile;   // first query row (within the batch) of this CTA
   ntiles = (!single && p.Nq - q0 > kTile) ? 2 : 1;                // second query tile present?
   return q0 < p.Nq;
+}
+
+__device__ __forceinline__ bool fmha_work(const FmhaParams& p, int& b, int& h, int& q0, int& ntiles) {
+  return fmha_item(p, static_cast<int>(blockIdx.x), b, h, q0, ntiles);
 }
 
 // smem layout (offsets from the 1024-aligned base): control words, 2 Q tiles, the K ring, the V ring (P lives in TMEM)
@@ -433,6 +437,391 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
 }
 
 
+
+#ifdef UDT_TUNING
+// ------------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (tuning builds only, UDT_FMHA_PERSIST=1) — measured on B200: correct on the first run (all accuracy cases incl.
+// ragged lengths, the 12 parity tests) and NOT faster: 4096 tokens 230.7 vs 227.7 us, 1024 tokens 45.4 vs 42.7, 256 tokens
+// 15.4 vs 12.6, batch-32 shape (35 items per CTA) 1745 vs 1746 us.  The per-item start-up it was built to hide is therefore not
+// launch / allocation / first-load latency between CTAs (that would have shown at 35 items per CTA); what remains per item is
+// inherent — the two-pass first tile, the output epilogue, the refill of the score pipeline.
+// PERSISTENT variant of the kernel above (same roles, same softmax code): one CTA per SM walks the work items
+// blockIdx.x, blockIdx.x + gridDim.x, ... and every barrier phase, the score-buffer rotation and the K / V ring simply continue
+// across items, so the next item's Q / K / V loads and first score MMAs run while the warpgroups still finish the current
+// item, and the ~8 k clk a CTA of the kernel above spends on launch, TMEM allocation, the first loads and its drain are paid
+// once per SM instead of once per item.  Items with the same number of query tiles form an EPOCH; at an epoch boundary (the
+// single-tile items of the tail wave, ragged sequence lengths) the CTA drains and re-initialises its barriers.
+// Extra state against the kernel above: a second Q buffer (Q of item e+1 is loaded when every score MMA of item e-1 has
+// completed), o_free[t] (warpgroup t has read O_t of the previous item: the first P V of the next may overwrite it).
+constexpr int kPkOffQ = 1024;                               // two Q buffers of two tiles
+constexpr int kPkOffK = kPkOffQ + 4 * kTileBytes;
+constexpr int kPkOffV = kPkOffK + kKvStages * kTileBytes;
+constexpr int kPkSmemBytes = kPkOffV + kKvStages * kTileBytes + 1024;
+
+// cursor over the computations of an epoch: item e, key tile j, query tile t; g = e * nkv + j (key tiles since the epoch began)
+struct PkCursor {
+  int c, e, j, t, g, stage, kvphase, b, u;
+  __device__ __forceinline__ void init() { c = e = j = t = g = stage = kvphase = b = u = 0; }
+  __device__ __forceinline__ void advance(int ntiles, int nkv) {
+    ++c;
+    if (++b == kSBufs) { b = 0; ++u; }
+    if (++t == ntiles) {
+      t = 0;
+      ++g;
+      if (++stage == kKvStages) { stage = 0; kvphase ^= 1; }
+      if (++j == nkv) { j = 0; ++e; }
+    }
+  }
+};
+
+__global__ void __launch_bounds__(kThreads, 1) udt_fmha_pk_kernel(const __grid_constant__ FmhaParams p) {
+  constexpr int kPoly = 0;
+  griddep_launch();   // PDL: let the next kernel's prologue start
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base = smem_raw + (base_addr - raw_addr);
+
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(base + kOffCtrl);   // [2]
+  uint64_t* kv_full = q_full + 2;            // [kKvStages]
+  uint64_t* s_full = kv_full + kKvStages;    // [kSBufs]
+  uint64_t* pv_done = s_full + kSBufs;       // [kSBufs]
+  uint64_t* p_full = pv_done + kSBufs;       // [2]
+  uint64_t* o_full = p_full + 2;             // [2]
+  uint64_t* o_free = o_full + 2;             // [2]   warpgroup t has read O_t of the item it just finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkv = (p.Nkv + kTile - 1) / kTile;
+  const int G = static_cast<int>(gridDim.x);
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+  }
+  if (warp == 8) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();     // PDL: q / k / v are produced by the previous kernel
+
+  bool first_epoch = true;
+  int L = static_cast<int>(blockIdx.x);
+  while (L < p.num_items) {
+    int b0, h0, q00, ntiles;
+    if (!fmha_item(p, L, b0, h0, q00, ntiles)) {   // odd tile count: the second half of a split pair does not exist
+      L += G;
+      continue;
+    }
+    int E = 1;                                     // items of this epoch: L, L + G, ... with the same number of query tiles
+    for (;;) {
+      const int Ln = L + E * G;
+      int bb, hh, qq, nt;
+      if (Ln >= p.num_items || !fmha_item(p, Ln, bb, hh, qq, nt) || nt != ntiles) break;
+      ++E;
+    }
+    // ---- (re)initialise the barriers: everybody has left the previous epoch, none of its phases is pending
+    if (!first_epoch) {
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+    if (threadIdx.x == 0) {
+      uint64_t* bars = q_full;
+      if (!first_epoch)
+        for (int i = 0; i < 2 + kKvStages + 2 * kSBufs + 6; ++i) mbar_inval(&bars[i]);
+      for (int i = 0; i < 2; ++i) mbar_init(&q_full[i], 1);
+      for (int i = 0; i < kKvStages; ++i) mbar_init(&kv_full[i], 1);
+      for (int i = 0; i < kSBufs; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&pv_done[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&p_full[i], 128);
+        mbar_init(&o_full[i], 1);
+        mbar_init(&o_free[i], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncthreads();
+    first_epoch = false;
+    const int ncomp = E * nkv * ntiles;            // computations of the epoch
+
+    if (warp == 9) {
+      // ---------------------------------------------------------------- score issuer + TMA producer
+      const bool issuer = elect_one();
+      const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false);
+      const int T = E * nkv;                       // key tiles of the epoch
+      int le = 0, lj = 0, ls = 0, lb = b0, lh = h0, loaded = 0;   // (elected lane) next key tile to load: item, tile, stage, its batch / head
+      auto load_q = [&](int e) {
+        int bb, hh, qq, nt;
+        fmha_item(p, L + e * G, bb, hh, qq, nt);
+        uint64_t* bar = &q_full[e & 1];
+        mbar_expect_tx(bar, static_cast<uint32_t>(ntiles * kTileBytes));
+        for (int t = 0; t < ntiles; ++t)
+          tma_load_2d(&p.mapQ, bar, base + kPkOffQ + ((e & 1) * 2 + t) * kTileBytes, hh * kD, bb * p.Nq + qq + t * kTile);
+      };
+      auto load_next_kv = [&]() {
+        mbar_expect_tx(&kv_full[ls], 2u * kTileBytes);
+        tma_load_2d(&p.mapK, &kv_full[ls], base + kPkOffK + ls * kTileBytes, lh * kD, lb * p.Nkv + lj * kTile);
+        tma_load_2d(&p.mapV, &kv_full[ls], base + kPkOffV + ls * kTileBytes, lh * kD, lb * p.Nkv + lj * kTile);
+        ++loaded;
+        if (++ls == kKvStages) ls = 0;
+        if (++lj == nkv) {
+          lj = 0;
+          if (++le < E) {
+            int qq, nt;
+            fmha_item(p, L + le * G, lb, lh, qq, nt);
+          }
+        }
+      };
+      if (issuer) {
+        load_q(0);
+        if (E > 1) load_q(1);
+        while (loaded < kKvStages && loaded < T) load_next_kv();
+      }
+      __syncwarp();
+      PkCursor ks, kd;   // kd trails ks by kSBufs computations: the previous user of the score buffer ks is about to overwrite
+      ks.init();
+      kd.init();
+      for (; ks.c < ncomp; ks.advance(ntiles, nkv)) {
+        if (ks.t == 0) {
+          mbar_wait(&kv_full[ks.stage], static_cast<uint32_t>(ks.kvphase));                       // K_j
+          if (ks.j == 0) mbar_wait(&q_full[ks.e & 1], static_cast<uint32_t>((ks.e >> 1) & 1));    // Q of a new item
+        }
+        if (ks.c >= kSBufs) {
+          // kd enters item e >= 1: every P V — hence every score MMA — of item e-1 has completed, its Q buffer takes item e+1
+          if (kd.j == 0 && kd.t == 0 && kd.e >= 1 && kd.e + 1 < E && issuer) load_q(kd.e + 1);
+          mbar_wait(&pv_done[kd.b], static_cast<uint32_t>(kd.u & 1));
+          if (kd.t == ntiles - 1 && issuer && loaded < T) load_next_kv();   // a key tile is finished: its stage takes the next one
+          kd.advance(ntiles, nkv);
+        }
+        tc_fence_after();
+        if (issuer) {
+          const uint64_t dq = umma_desc_kmajor_sw128(base_addr + kPkOffQ + ((ks.e & 1) * 2 + ks.t) * kTileBytes);
+          const uint64_t dk = umma_desc_kmajor_sw128(base_addr + kPkOffK + ks.stage * kTileBytes);
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk)
+            umma_f16_ss(tmem_base + kColS + ks.b * 128, dq + static_cast<uint64_t>(kk * 2), dk + static_cast<uint64_t>(kk * 2),
+                        idesc_s, kk != 0 ? 1u : 0u);
+          umma_commit(&s_full[ks.b]);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 8) {
+      // ---------------------------------------------------------------- PV issuer
+      const bool issuer = elect_one();
+      const uint32_t idesc_o = umma_idesc_f16(128, 64, false, true);  // B = V is MN-major
+      PkCursor kp;
+      kp.init();
+      for (; kp.c < ncomp; kp.advance(ntiles, nkv)) {
+        if (kp.j == 0 && kp.e > 0) mbar_wait(&o_free[kp.t], static_cast<uint32_t>((kp.e - 1) & 1));   // O_t of the previous item has been read out
+        mbar_wait(&p_full[kp.t], static_cast<uint32_t>(kp.g & 1));
+        if (kp.t == 0) mbar_wait(&kv_full[kp.stage], static_cast<uint32_t>(kp.kvphase));
+        tc_fence_after();
+        if (issuer) {
+          const uint32_t v_addr = base_addr + kPkOffV + kp.stage * kTileBytes;
+          const uint32_t p_tmem = tmem_base + kColS + kp.b * 128;
+#pragma unroll
+          for (int kk = 0; kk < kTile / 16; ++kk) {
+            const uint64_t dv = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, 8192);
+            umma_f16_ts(tmem_base + kColO + kp.t * 64, p_tmem + kk * 8, dv, idesc_o, (kp.j | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&pv_done[kp.b]);
+          umma_commit(&o_full[kp.t]);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ---------------------------------------------------------------- softmax warpgroups (code of the kernel above)
+      const int t = warp >> 2;
+      UDT_FSTAMP_DECL;
+      if (t < ntiles) {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t o_addr = tmem_base + lane_base + kColO + t * 64;
+        const float sl2 = p.scale_log2;
+        int sb = t, su = 0;   // S buffer / use count of this warpgroup's next computation: continue across the items of the epoch
+        for (int e = 0; e < E; ++e) {
+          int b, h, q0, nt_unused;
+          fmha_item(p, L + e * G, b, h, q0, nt_unused);
+          const int g0 = e * nkv;   // key tiles before this item: p_full / o_full phases are counted per epoch
+          float m_ref = -INFINITY, l = 0.0f;
+          // rescale the running output (and row sum) when the reference maximum moves; O_t must be stable
+          auto rescale = [&](bool need, float m_tile, int j) {
+            const float m_new = need ? m_tile : m_ref;
+            const float alpha = need ? ex2_approx(m_ref - m_new) : 1.0f;  // m_ref = -inf on the first tile -> 0
+            l *= alpha;
+            if (j > 0) {
+              mbar_wait(&o_full[t], static_cast<uint32_t>((g0 + j - 1) & 1));
+              tc_fence_after();
+    #pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(o_addr + c * 32, v);
+                tmem_ld_wait();
+    #pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                tmem_st32(o_addr + c * 32, v);
+              }
+              tmem_st_wait();
+            }
+            m_ref = m_new;
+          };
+
+          for (int j = 0; j < nkv; ++j) {
+            UDT_FSTAMP(j, 0);
+            mbar_wait(&s_full[sb], static_cast<uint32_t>(su & 1));
+            tc_fence_after();
+            UDT_FSTAMP(j, 1);
+            const uint32_t s_addr = tmem_base + lane_base + kColS + sb * 128;
+            const int key_lim = p.Nkv - j * kTile;  // keys >= key_lim of this tile are padding (only on the last tile)
+            const bool partial = key_lim < kTile;
+            float rowsum = 0.0f;
+            bool replay = (j == 0) || partial;      // first / ragged tile: maximum first, then the exponentials
+            // 32 probabilities (keys [32*ch, 32*ch+32) of this tile) -> fp16 -> this row's swizzled slots of the P buffer;
+            // the stores interleave with the exponentials of the following chunk
+            uint32_t pall[64];                      // the tile's probabilities, fp16 pairs (key 2i | key 2i+1)
+            auto store_chunk = [&](const uint32_t (&pk)[16], int ch) {
+    #pragma unroll
+              for (int i = 0; i < 16; ++i) pall[ch * 16 + i] = pk[i];
+            };
+            if (!replay) {
+              // ---- single pass: exponentials against the current reference, written to the P buffer right away.  No
+              // maximum is tracked: every probability is bounded by 2^8 unless the tile's row sum exceeds 2^8, so a row sum
+              // above that bound (rare: the reference would have to be stale by almost the whole lazy margin) sends the tile
+              // through the two-pass path, which overwrites the optimistic P (nobody reads it before p_full).
+              uint32_t va[32], vb[32];
+              auto exp_chunk = [&](const uint32_t (&vv)[32], int ch) {
+                uint32_t pk[16];
+    #pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  float p0 = fmaf(__uint_as_float(vv[i]), sl2, -m_ref);
+                  float p1 = fmaf(__uint_as_float(vv[i + 1]), sl2, -m_ref);
+                  if (!UDT_FDBG(1)) {
+                    p0 = (kPoly > 0 && (i % kPoly) == kPoly - 1) ? ex2_poly(p0) : ex2_approx(p0);
+                    p1 = (kPoly > 0 && ((i + 1) % kPoly) == kPoly - 1) ? ex2_poly(p1) : ex2_approx(p1);
+                  }
+                  rowsum += p0 + p1;
+                  pk[i >> 1] = pack_half2(p0, p1);
+                }
+                if (!UDT_FDBG(2)) store_chunk(pk, ch);
+              };
+              tmem_ld32(s_addr, va);
+              tmem_ld_wait_dep(va);
+              UDT_FSTAMP(j, 2);
+              tmem_ld32(s_addr + 32, vb);      // the next 32 columns fly during the math
+              exp_chunk(va, 0);
+              UDT_FSTAMP(j, 3);
+              tmem_ld_wait_dep(vb);
+              tmem_ld32(s_addr + 64, va);
+              exp_chunk(vb, 1);
+              tmem_ld_wait_dep(va);
+              tmem_ld32(s_addr + 96, vb);
+              exp_chunk(va, 2);
+              tmem_ld_wait_dep(vb);
+              UDT_FSTAMP(j, 4);
+              exp_chunk(vb, 3);
+              UDT_FSTAMP(j, 5);
+              replay = __any_sync(0xffffffffu, !(rowsum <= 256.0f)) && !UDT_FDBG(3);   // also catches inf / nan
+            }
+            if (replay) {
+              // ---- two passes: row maximum of the raw scores, reference update (+ O rescale), exponentials
+              uint32_t v[32];
+              float mx = -INFINITY;
+    #pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                tmem_ld32(s_addr + ch * 32, v);
+                tmem_ld_wait();
+    #pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (!partial || ch * 32 + i < key_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+              }
+              const float m_tile = mx * sl2;
+              const bool need = m_tile > m_ref + kLazyThreshold;
+              if (__any_sync(0xffffffffu, need)) rescale(need, m_tile, j);
+              rowsum = 0.0f;
+    #pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                tmem_ld32(s_addr + ch * 32, v);
+                tmem_ld_wait();
+                uint32_t pk[16];
+    #pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -m_ref));
+                  float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -m_ref));
+                  if (partial) {
+                    const int k0 = ch * 32 + i;
+                    if (k0 >= key_lim) p0 = 0.0f;
+                    if (k0 + 1 >= key_lim) p1 = 0.0f;
+                  }
+                  rowsum += p0 + p1;
+                  pk[i >> 1] = pack_half2(p0, p1);
+                }
+                store_chunk(pk, ch);
+              }
+            }
+            l += rowsum;
+            // ---- P -> TMEM, over the first 64 columns of the (fully consumed) score buffer: the PV MMA reads it as its A operand
+            {
+              uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pall[0]);
+              uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pall[32]);
+              tmem_st32(s_addr, lo);
+              tmem_st32(s_addr + 32, hi);
+              tmem_st_wait();
+            }
+            UDT_FSTAMP(j, 6);
+            // observe every o_full phase (the wait is almost always already satisfied: P_t V_{j-1} ran during this tile's
+            // exponentials); a parity wait that skipped phases would be ambiguous in rescale() and at the end
+            if (j > 0) mbar_wait(&o_full[t], static_cast<uint32_t>((g0 + j - 1) & 1));
+            tc_fence_before();         // TMEM reads of S / writes of P, O_t ordered before the arrive
+            mbar_arrive(&p_full[t]);
+            UDT_FSTAMP(j, 7);
+            sb += ntiles;
+            if (sb >= kSBufs) { sb -= kSBufs; ++su; }
+          }
+          mbar_wait(&o_full[t], static_cast<uint32_t>((g0 + nkv - 1) & 1));
+          tc_fence_after();
+          const int qrow = q0 + t * kTile + row;
+          const float inv = 1.0f / l;
+          uint4* o4 = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.Nq + min(qrow, p.Nq - 1)) * p.ldo + h * kD);
+    #pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(o_addr + c * 32, v);
+            tmem_ld_wait();
+            if (qrow < p.Nq) {
+    #pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 ov;
+                ov.x = pack_half2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+                ov.y = pack_half2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+                ov.z = pack_half2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+                ov.w = pack_half2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+                o4[c * 4 + g] = ov;
+              }
+            }
+          }
+          tc_fence_before();         // the tcgen05.ld of O_t ordered before the arrive
+          mbar_arrive(&o_free[t]);
+        }
+      }
+    }
+    L += E * G;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+#endif  // UDT_TUNING (persistent variant)
 
 #ifdef UDT_TUNING
 // ------------------------------------------------------------------------------------------------------------------
@@ -1070,6 +1459,21 @@ extern "C" int udt_fmha_fwd(const void* q, const void* k, const void* v, void* o
     }
     udt_host::launch_pdl(udt_fmha_w4_kernel, dim3(grid), dim3(kW4Threads), kW4SmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("udt_fmha_fwd (w4)");
+  }
+#endif
+  p.num_items = static_cast<int32_t>(grid.x);
+#ifdef UDT_TUNING
+  static const int persist = tune_int("UDT_FMHA_PERSIST", 0);
+  if (persist) {   // persistent CTAs: one per SM, items round-robin
+    static bool pk_attr = false;
+    if (!pk_attr) {
+      cudaError_t e = cudaFuncSetAttribute(udt_fmha_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmemBytes);
+      if (e != cudaSuccess) return fail(UDT_ERR_LAUNCH, "cudaFuncSetAttribute(fmha persistent smem): %s", cudaGetErrorString(e));
+      pk_attr = true;
+    }
+    const unsigned g = grid.x < static_cast<unsigned>(nsm) ? grid.x : static_cast<unsigned>(nsm);
+    udt_host::launch_pdl(udt_fmha_pk_kernel, dim3(g), dim3(kThreads), kPkSmemBytes, reinterpret_cast<cudaStream_t>(stream), p);
+    return check_launch("udt_fmha_fwd (persistent)");
   }
 #endif
   static const int poly = tune_int("UDT_FMHA_POLY", 0);
