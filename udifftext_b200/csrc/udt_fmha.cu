@@ -308,20 +308,6 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 16; ++i) pall[ch * 16 + i] = pk[i];
         };
-        if (j == 0 && !partial) {
-          // ---- first key tile: take the reference from the row's first 32 keys and go through the single pass like every
-          // other tile (l = 0 and O_t is not written yet: nothing to rescale).  The row-sum bound below still catches a row
-          // whose maximum lies more than 2^8 above that reference and replays the tile with the exact maximum.  Saves one of
-          // the first tile's two passes over TMEM: 1024 tokens 43.0 -> 41.4 us, 256 tokens 12.5 -> 11.5 us (4096 tokens: unchanged).
-          uint32_t v[32];
-          tmem_ld32(s_addr, v);
-          tmem_ld_wait();
-          float mx = __uint_as_float(v[0]);
-#pragma unroll
-          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          m_ref = mx * sl2;
-          replay = false;
-        }
         if (!replay) {
           // ---- single pass: exponentials against the current reference, written to the P buffer right away.  No
           // maximum is tracked: every probability is bounded by 2^8 unless the tile's row sum exceeds 2^8, so a row sum
