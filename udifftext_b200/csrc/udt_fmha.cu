@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
       const float sl2 = p.scale_log2;
       float m_ref = -INFINITY, l = 0.0f;
       int sb = t, su = 0;   // S buffer / use count of this warpgroup's next computation (c = j * ntiles + t)
+#ifdef UDT_IGEMM_TRACE
+      int cnt_replay = 0, cnt_rescale = 0;   // UDT_FMHA_DEBUG & 32: replays of the single pass / O rescales seen by this warp
+#endif
 
       // rescale the running output (and row sum) when the reference maximum moves; O_t must be stable
       auto rescale = [&](bool need, float m_tile, int j) {
@@ -346,6 +349,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
           exp_chunk(vb, 3);
           UDT_FSTAMP(j, 5);
           replay = __any_sync(0xffffffffu, !(rowsum <= 256.0f)) && !UDT_FDBG(3);   // also catches inf / nan
+#ifdef UDT_IGEMM_TRACE
+          cnt_replay += replay ? 1 : 0;
+#endif
         }
         if (replay) {
           // ---- two passes: row maximum of the raw scores, reference update (+ O rescale), exponentials
@@ -362,6 +368,9 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
           const float m_tile = mx * sl2;
           const bool need = m_tile > m_ref + kLazyThreshold;
           if (__any_sync(0xffffffffu, need)) rescale(need, m_tile, j);
+#ifdef UDT_IGEMM_TRACE
+          cnt_rescale += (j > 0 && __any_sync(0xffffffffu, need)) ? 1 : 0;
+#endif
           rowsum = 0.0f;
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
@@ -425,6 +434,10 @@ __global__ void __launch_bounds__(kThreads, 1) udt_fmha_ts_kernel(const __grid_c
         }
       }
       UDT_FSTAMP_DUMP(nkv);
+#ifdef UDT_IGEMM_TRACE
+      if ((p.debug & 32) && lane == 0 && (blockIdx.x % 37) == 0)
+        printf("FCNT nkv %d heads %d cta %d warp %d replays %d rescales %d\n", nkv, p.heads, static_cast<int>(blockIdx.x), warp, cnt_replay, cnt_rescale);
+#endif
     }
   }
 
