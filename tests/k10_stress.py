@@ -1,4 +1,4 @@
-"""K10 flake hunt: same inputs, many launches (fresh H2D copies each time like the test); report any launch whose output differs
+"""(test infrastructure: uses the oracle as the checker, hence under tests/)  K10 flake hunt: same inputs, many launches (fresh H2D copies each time like the test); report any launch whose output differs
 from the first one or from the CPU reference."""
 import sys, torch
 import torch.nn.functional as F

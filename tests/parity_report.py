@@ -2,7 +2,7 @@
 """Measured parity of the product against the TF32-free fp32 oracle, stage by stage, written to a JSON file
 (committed as profiles/parity_r02.json).  Runs on the GPU box:
 
-  python scripts/parity_report.py [--out gpurun_out/parity.json] [--study]
+  python tests/parity_report.py [--out gpurun_out/parity.json] [--study]
 
 Configurations: BASELINE configs[1] = C2 (batch 4, 512x512, 50 steps, 8-char strings) with per-step guided-eps errors
 (free-running and teacher-forced on the oracle's x), C1 (golden of the unmodified reference's CPU run), tiny.
@@ -19,7 +19,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # parity_util
 
 import torch
 import torch.nn.functional as F

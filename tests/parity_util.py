@@ -1,7 +1,7 @@
 """Shared parity harness (TEST INFRASTRUCTURE): runs one `predict` of the product step by step next to the fp32 oracle
 (oracle/restated.py) on the same device, seeds and weights, and reports the error of every stage.
 
-Used by tests/test_parity_c2_gpu.py (gates) and scripts/parity_report.py (writes profiles/parity_r02.json).  The oracle
+Used by tests/test_parity_c2_gpu.py (gates) and tests/parity_report.py (writes profiles/parity_r02.json).  The oracle
 is evaluated with TF32 disabled (`fp32_oracle()`): TF32 has fp16's 10-bit mantissa, so a TF32 "fp32" oracle carries an
 error of the size being measured.
 """

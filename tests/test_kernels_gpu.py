@@ -303,7 +303,7 @@ def test_vae_sample_pack_and_pointwise_affine(udt_lib):
     # (Root cause of the "rare cold-box mismatch" this test once retried: its first version compared against an fp32 CPU
     # evaluation, whose exp / mul-add rounding depends on the host CPU's vector path; with sd ~ 2e4 one ulp of sd * noise is
     # 4e-3, i.e. up to 2e-4 of the old metric.  The kernel itself is deterministic — launches are bit-identical below and
-    # over 400 fresh uploads in scripts/k10_stress.py — so there is nothing to retry.)
+    # over 400 fresh uploads in tests/k10_stress.py — so there is nothing to retry.)
     m8 = F.interpolate(mask.double(), scale_factor=0.125, mode="bilinear")
     sd64 = torch.exp(0.5 * torch.clamp(moments[:, 4:].double(), -30.0, 20.0))
     refs = (torch.cat([m8, 0.18215 * R.posterior_sample(moments.double(), n_c.double())], dim=1),

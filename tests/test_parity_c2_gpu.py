@@ -3,7 +3,7 @@ strings — against the fp32 oracle (oracle/restated.py, TF32 disabled) on the s
 product's public path (conditioner -> get_init_noise -> CUDA-graphed StepRunner -> decode).
 
 Gates: decoded pixels at the north-star tolerance 1e-3 (relative L2), every other stage at 1.5x the value measured on
-B200 and recorded in profiles/parity_r02.json (scripts/parity_report.py); per-step guided-eps checks at steps
+B200 and recorded in profiles/parity_r02.json (tests/parity_report.py); per-step guided-eps checks at steps
 {0, 1, n/2, n-1}, free-running and teacher-forced on the oracle's x.  fp16 storage bounds what is
 reachable: the ORACLE ITSELF with fp16-rounded weights and activations sits at 7.9e-4 on the pixels of this config.
 """

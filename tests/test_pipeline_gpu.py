@@ -56,7 +56,7 @@ def test_tiny_predict_matches_reference(tiny_engine):
     ez, ep = _rel(z, gold["predict_z"]), _rel(img, gold["predict_pixels"])
     print(f"tiny predict: z rel-L2 {ez:.3e}, pixels rel-L2 {ep:.3e}, max-abs {(img.cpu() - gold['predict_pixels']).abs().max():.3e}")
     assert ez < 3.3e-3 and ep < 1.7e-3      # 1.5 x measured on B200 (2.17e-3 / 1.11e-3; 3 steps of the tiny network:
-    # the oracle itself with fp16-rounded operands sits at 1.2e-3 here — scripts/parity_report.py)
+    # the oracle itself with fp16-rounded operands sits at 1.2e-3 here — tests/parity_report.py)
     # a second request replays the captured CUDA graph: bit-identical
     torch.manual_seed(gold["predict_seed"])
     img2, z2 = api.predict(cfgs, tiny_engine, sampler, synth.synthetic_batch(gold["predict_config_id"], 2, 64, 64, None))
