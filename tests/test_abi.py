@@ -83,3 +83,33 @@ def test_production_kernels_read_no_environment():
     assert "getenv" in block
     os.environ.pop("UDT_TRACE", None)
     assert "-DUDT_TUNING" not in build._flags()
+
+
+def test_only_test_infrastructure_touches_the_oracle():
+    """oracle/ is the checker, never the product: nothing in the package, the scripts or the C sources may import, link or
+    execute it; outside tests/ only __graft_entry__.smoke() and bench.py's baseline legs do."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|oracle[/.](restated|parseq_restated|ref_import|make_golden)", re.M)
+    offenders = []
+    for sub in ("udifftext_b200", "scripts", "include"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".sh", ".cpp")):
+                    continue
+                path = os.path.join(dirpath, f)
+                text = open(path, encoding="utf-8", errors="ignore").read()
+                if re.search(r"^\s*(from\s+oracle\b|import\s+oracle\b)", text, re.M):
+                    offenders.append(os.path.relpath(path, root))
+    assert offenders == [], offenders
+    # the two allowed importers outside tests/ use it only in the legs the contract names
+    imp = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    for name, allowed in (("__graft_entry__.py", {"smoke"}),
+                          ("bench.py", {"cpu_reference_sample", "run_reference", "gpu_library_baseline"})):
+        text = open(os.path.join(root, name)).read()
+        hits = list(imp.finditer(text))
+        assert hits, name
+        for m in hits:
+            fn = re.findall(r"^def\s+(\w+)", text[: m.start()], re.M)[-1]
+            assert fn in allowed, (name, fn)
